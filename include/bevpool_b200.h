@@ -1,0 +1,154 @@
+/*
+ * bevpool_b200 — C ABI of the B200-native (sm_100a) camera->BEV view transform.
+ *
+ * This is the drop-in boundary. Every entry point takes plain device pointers and
+ * sizes (no torch types), launches hand-written CUDA kernels asynchronously on the
+ * stream the caller passes (a cudaStream_t cast to void*; NULL = legacy default
+ * stream) and returns 0 or a negative bevpool_status / positive cudaError_t.
+ * Nothing here synchronises the device and nothing falls back to the CPU.
+ *
+ * Reference interfaces replaced (paths relative to
+ * /root/reference/projects/mmdet3d_plugin):
+ *
+ *   bevpool_v2_forward            ops/bev_pool_v2/src/bev_pool.cpp:30-57   bev_pool_v2_forward(...)
+ *                                 -> src/bev_pool_cuda.cu:21-48,125-131    bev_pool_v2_kernel
+ *   bevpool_v2_backward           ops/bev_pool_v2/src/bev_pool.cpp:74-104  bev_pool_v2_backward(...)
+ *                                 -> src/bev_pool_cuda.cu:67-121,133-140   bev_pool_grad_kernel
+ *   bevpool_v2_backward_regroup   ops/bev_pool_v2/bev_pool.py:47-57        argsort by ranks_feat + run-length
+ *   bevpool_geometry              bevfusion/detectors/cam_stream_lss_bevpoolv2.py:244-251  get_geometry
+ *   bevpool_prepare_v2            same file :294-351                        voxel_pooling_prepare_v2
+ *   bevpool_v2_forward_dense /    the fused forms of the above used by the view-transform shim:
+ *   bevpool_v2_backward_dense     bev_pool.py:27 (zeros) + :29 (kernel) + :91 (permute) in one pass;
+ *                                 bev_pool.py:47-57,67-70 (argsort, zeros, kernel) in one pass
+ *
+ * Argument order note: like the reference's native entry points, interval_lengths
+ * precedes interval_starts here (bev_pool.cpp:37-38), the opposite of the Python API.
+ */
+#ifndef BEVPOOL_B200_H_
+#define BEVPOOL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BEVPOOL_B200_ABI_VERSION 1
+
+/* element type of depth / feat / out / grads */
+enum { BEVPOOL_F32 = 0, BEVPOOL_BF16 = 1 };
+/* memory layout of the BEV grid tensor */
+enum {
+  BEVPOOL_LAYOUT_BZYXC = 0, /* channels last: what QuickCumsumCuda.forward returns (bev_pool.py:27) */
+  BEVPOOL_LAYOUT_BCZYX = 1  /* what bev_pool_v2() returns after its permute (bev_pool.py:91)      */
+};
+/* negative status codes (positive values are cudaError_t) */
+enum {
+  BEVPOOL_OK = 0,
+  BEVPOOL_ERR_BAD_ARG = -1,      /* null pointer, negative size, unsupported dtype/layout      */
+  BEVPOOL_ERR_BAD_CHANNELS = -2, /* c <= 0                                                     */
+  BEVPOOL_ERR_WORKSPACE = -3,    /* workspace too small (see *_workspace_bytes)                */
+  BEVPOOL_ERR_OVERFLOW = -4      /* a rank/index would not fit the int32 the API mandates      */
+};
+
+int bevpool_b200_abi_version(void);
+/* human-readable text for a code returned by any function below (static storage) */
+const char* bevpool_b200_strerror(int code);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+int64_t bevpool_b200_launch_count(void);
+
+/* ------------------------------------------------------------------ pooling, reference contract
+ * out[ranks_bev[s_k]*c + ch] = sum_i depth[ranks_depth[s_k+i]] * feat[ranks_feat[s_k+i]*c + ch]
+ * `out` is [B,Z,Y,X,C] and PRE-ZEROED by the caller; only touched voxels are written.
+ * The per-channel sum runs in sorted point order with fused multiply-add, i.e. it is
+ * bit-identical to the reference kernel for fp32. */
+int bevpool_v2_forward(const void* depth, const void* feat, void* out,
+                       const int32_t* ranks_depth, const int32_t* ranks_feat, const int32_t* ranks_bev,
+                       const int32_t* interval_lengths, const int32_t* interval_starts,
+                       int64_t n_points, int64_t n_intervals, int c, int dtype, void* stream);
+
+/* Rank arrays here are the ones REGROUPED by ranks_feat and the intervals are the
+ * backward intervals (one per feature pixel), exactly what bev_pool.py:47-57 builds.
+ * depth_grad / feat_grad are PRE-ZEROED by the caller. out_grad is [B,Z,Y,X,C]. */
+int bevpool_v2_backward(const void* out_grad, void* depth_grad, void* feat_grad,
+                        const void* depth, const void* feat,
+                        const int32_t* ranks_depth, const int32_t* ranks_feat, const int32_t* ranks_bev,
+                        const int32_t* interval_lengths, const int32_t* interval_starts,
+                        int64_t n_points, int64_t n_intervals, int c, int dtype, void* stream);
+
+/* Stable regrouping of the three rank arrays by ranks_feat and run-length segmentation.
+ * Outputs have n_points (ranks) / n_points (intervals, worst case) capacity;
+ * *n_intervals_bp_dev (device int32) receives the interval count. */
+size_t bevpool_v2_backward_regroup_workspace_bytes(int64_t n_points);
+int bevpool_v2_backward_regroup(const int32_t* ranks_depth, const int32_t* ranks_feat, const int32_t* ranks_bev,
+                                int64_t n_points, int32_t max_ranks_feat,
+                                int32_t* ranks_depth_bp, int32_t* ranks_feat_bp, int32_t* ranks_bev_bp,
+                                int32_t* interval_starts_bp, int32_t* interval_lengths_bp,
+                                int32_t* n_intervals_bp_dev,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ geometry
+ * coor[b,n,d,h,w,:] = rots[b,n] . (u*d, v*d, d) + trans[b,n] with every multiply/add rounded
+ * separately (no FMA contraction), matching the reference's CPU result bit for bit.
+ * frustum is [D,H,W,3] fp32 (the reference's nn.Parameter), rots [BN,3,3], trans [BN,3]. */
+int bevpool_geometry(const float* frustum, const float* rots, const float* trans, float* coor,
+                     int bn, int d, int hw, void* stream);
+
+/* ------------------------------------------------------------------ prepare
+ * Grid description shared by the prepare / dense entry points. */
+typedef struct {
+  int32_t b, n, d, h, w;  /* frustum batch shape: B frames x N cameras x D bins x H x W            */
+  int32_t nx[3];          /* X, Y, Z voxel counts                                                   */
+  float lo[3];            /* fp32 (bx - dx/2), computed by the caller in fp32 as the reference does */
+  float dx[3];            /* voxel size                                                             */
+} bevpool_grid_t;
+
+size_t bevpool_prepare_v2_workspace_bytes(const bevpool_grid_t* g);
+
+/* voxel_pooling_prepare_v2. Exactly one of (coor) or (frustum, rots, trans) is given:
+ *   coor != NULL  : reads the materialised [B,N,D,H,W,3] fp32 coordinates (the unchanged API);
+ *   coor == NULL  : geometry is fused, coordinates are never written to memory.
+ * Outputs (capacity P0 = b*n*d*h*w each for ranks_*, min(P0, B*V) for intervals):
+ *   ranks_bev/ranks_depth/ranks_feat (sorted by ranks_bev, ties ascending ranks_depth),
+ *   interval_starts/interval_lengths, counts_dev[0] = P (kept points), counts_dev[1] = I.
+ *   point_rank (optional, may be NULL): int32[P0] voxel rank of every frustum point, -1 if
+ *   dropped — the inverse table the sort-free backward uses.
+ * No host synchronisation: the caller reads counts_dev when it needs exact lengths. */
+int bevpool_prepare_v2(const float* coor, const float* frustum, const float* rots, const float* trans,
+                       const bevpool_grid_t* g,
+                       int32_t* ranks_bev, int32_t* ranks_depth, int32_t* ranks_feat,
+                       int32_t* interval_starts, int32_t* interval_lengths,
+                       int32_t* counts_dev, int32_t* point_rank,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ fused ("dense") pooling
+ * Forward that also zero-fills empty voxels and writes either layout directly.
+ * n_intervals is read from counts_dev[1] on the device when counts_dev != NULL (no host sync),
+ * else from the n_intervals argument. n_voxels_total = B*Z*Y*X, voxels_per_frame = Z*Y*X.
+ * `out` need NOT be zeroed. workspace holds the strip->interval table. */
+size_t bevpool_v2_forward_dense_workspace_bytes(int64_t n_voxels_total, int64_t voxels_per_frame);
+int bevpool_v2_forward_dense(const void* depth, const void* feat, void* out,
+                             const int32_t* ranks_depth, const int32_t* ranks_feat, const int32_t* ranks_bev,
+                             const int32_t* interval_lengths, const int32_t* interval_starts,
+                             int64_t n_intervals, const int32_t* counts_dev,
+                             int c, int64_t n_voxels_total, int64_t voxels_per_frame,
+                             int layout, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Sort-free backward for rank arrays that came from bevpool_prepare_v2: walks the D depth
+ * bins of every feature pixel through point_rank, writes EVERY element of depth_grad
+ * ([B,N,D,H,W], zeros for dropped points) and feat_grad ([B,N,H,W,C]) — no memset, no argsort.
+ * out_grad is [B,Z,Y,X,C] (use bevpool_grid_transpose for a [B,C,Z,Y,X] gradient). */
+int bevpool_v2_backward_dense(const void* out_grad, void* depth_grad, void* feat_grad,
+                              const void* depth, const void* feat, const int32_t* point_rank,
+                              int bn, int d, int hw, int c, int dtype, void* stream);
+
+/* [B,C,Z,Y,X] <-> [B,Z,Y,X,C] tile transpose (bev_pool.py:69 / :91 as one coalesced pass).
+ * to_channels_last != 0: src is BCZYX, dst is BZYXC; else the reverse. */
+int bevpool_grid_transpose(const void* src, void* dst, int b, int c, int64_t zyx,
+                           int to_channels_last, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEVPOOL_B200_H_ */

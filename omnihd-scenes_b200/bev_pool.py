@@ -1,0 +1,291 @@
+"""Host-side mirror of the reference operator module
+projects/mmdet3d_plugin/ops/bev_pool_v2/bev_pool.py (same names, argument order,
+return layout and None conventions) on top of the sm_100a C-ABI library.
+
+    bev_pool_v2(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                bev_feat_shape, interval_starts, interval_lengths) -> [B, C, Z, Y, X]
+    QuickCumsumCuda            reference-contract autograd Function -> [B, Z, Y, X, C]
+    TRTBEVPoolv2               inference wrapper + ONNX symbolic (mmdeploy::bev_pool_v2)
+
+What differs from the reference is only HOW: `bev_pool_v2` runs one fused kernel that
+zero-fills, pools and writes [B,C,Z,Y,X] directly (reference: new_zeros + kernel + permute,
+bev_pool.py:27,29,91); its backward is sort-free when the rank tensors are the ones returned
+by this package's `voxel_pooling_prepare_v2` (reference: argsort + where + two new_zeros per
+step, bev_pool.py:47-68) and otherwise regroups on the device with a radix sort.
+Errors are loud: wrong device/dtype/shape raise ValueError, a failing kernel raises
+BevPoolError; nothing falls back to PyTorch ops or the CPU.
+"""
+import weakref
+
+import torch
+
+from . import _lib
+
+__all__ = ['bev_pool_v2', 'TRTBEVPoolv2']
+
+
+# ----------------------------------------------------------------------------- helpers
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _dtype_code(t):
+    if t.dtype == torch.float32:
+        return _lib.F32
+    if t.dtype == torch.bfloat16:
+        return _lib.BF16
+    raise ValueError(f"unsupported dtype {t.dtype}")
+
+
+def _as_int(v):
+    # bev_feat_shape entries may be 0-dim (even CUDA) tensors: cam_stream_lss_bevpoolv2.py:283-285
+    return int(v.item()) if isinstance(v, torch.Tensor) else int(v)
+
+
+def _require_cuda(name, t):
+    if not isinstance(t, torch.Tensor):
+        raise ValueError(f"{name} must be a tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (bevpool_b200 has no CPU path)")
+
+
+def _canon_inputs(depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths):
+    """Casts of bev_pool.py:19-25. fp32 unless BOTH depth and feat are bf16 (explicit extension)."""
+    for n, t in (("depth", depth), ("feat", feat), ("ranks_depth", ranks_depth), ("ranks_feat", ranks_feat),
+                 ("ranks_bev", ranks_bev), ("interval_starts", interval_starts),
+                 ("interval_lengths", interval_lengths)):
+        _require_cuda(n, t)
+        if t.device != depth.device:
+            raise ValueError(f"{n} is on {t.device}, depth on {depth.device}")
+    if depth.dtype == torch.bfloat16 and feat.dtype == torch.bfloat16:
+        depth, feat = depth.contiguous(), feat.contiguous()
+    else:
+        depth, feat = depth.contiguous().float(), feat.contiguous().float()
+    ints = [t.contiguous().int() for t in (ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths)]
+    n_points = ints[0].numel()
+    if ints[1].numel() != n_points or ints[2].numel() != n_points:
+        raise ValueError("ranks_depth, ranks_feat and ranks_bev must have the same length")
+    if ints[3].numel() != ints[4].numel():
+        raise ValueError("interval_starts and interval_lengths must have the same length")
+    if feat.dim() < 1 or feat.shape[-1] <= 0:
+        raise ValueError("feat must be [..., C] with C > 0 (channels last)")
+    return (depth, feat) + tuple(ints)
+
+
+def _shape5(bev_feat_shape, feat):
+    if len(bev_feat_shape) != 5:
+        raise ValueError("bev_feat_shape must be (B, Z, Y, X, C)")
+    B, Z, Y, X, C = (_as_int(v) for v in bev_feat_shape)
+    if C != feat.shape[-1]:
+        raise ValueError(f"bev_feat_shape C={C} does not match feat channels {feat.shape[-1]}")
+    if min(B, Z, Y, X) < 0:
+        raise ValueError("negative bev_feat_shape")
+    if B * Z * Y * X >= 2 ** 31:
+        raise ValueError("B*Z*Y*X must fit int32 ranks")
+    return B, Z, Y, X, C
+
+
+# ----------------------------------------------------------------------------- plans
+class PreparePlan:
+    """Side information attached to the tensors `voxel_pooling_prepare_v2` returns.
+
+    point_rank[P0] (voxel rank of every frustum point, -1 = dropped) is the inverse table
+    that lets the backward walk a pixel's depth bins without sorting by ranks_feat.
+    """
+
+    def __init__(self, tensors, point_rank, bn, d, hw):
+        self.refs = [weakref.ref(t) for t in tensors]
+        self.versions = [t._version for t in tensors]
+        self.point_rank, self.bn, self.d, self.hw = point_rank, bn, d, hw
+
+    def matches(self, tensors):
+        return all(r() is t and t._version == v for r, t, v in zip(self.refs, tensors, self.versions))
+
+
+_PLANS = {}
+
+
+def register_plan(ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths, point_rank, bn, d, hw):
+    tensors = (ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths)
+    key = id(ranks_bev)
+    _PLANS[key] = PreparePlan(tensors, point_rank, bn, d, hw)
+    weakref.finalize(ranks_bev, _PLANS.pop, key, None)
+
+
+def _find_plan(ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths, depth, feat):
+    plan = _PLANS.get(id(ranks_bev))
+    if plan is None or not plan.matches((ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths)):
+        return None
+    if depth.numel() != plan.bn * plan.d * plan.hw or feat.numel() != plan.bn * plan.hw * feat.shape[-1]:
+        return None
+    return plan
+
+
+# ----------------------------------------------------------------------------- raw launches
+def _launch_forward(depth, feat, out, rd, rf, rb, starts, lengths):
+    lib = _lib.load()
+    _lib.check(lib.bevpool_v2_forward(_ptr(depth), _ptr(feat), _ptr(out), _ptr(rd), _ptr(rf), _ptr(rb),
+                                      _ptr(lengths), _ptr(starts), rd.numel(), starts.numel(), feat.shape[-1],
+                                      _dtype_code(feat), _stream()), "bevpool_v2_forward")
+
+
+def _launch_forward_dense(depth, feat, out, rd, rf, rb, starts, lengths, n_intervals, counts_dev, n_vox_total,
+                          vox_per_frame, layout):
+    lib = _lib.load()
+    ws_bytes = lib.bevpool_v2_forward_dense_workspace_bytes(n_vox_total, vox_per_frame)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=feat.device)
+    _lib.check(lib.bevpool_v2_forward_dense(_ptr(depth), _ptr(feat), _ptr(out), _ptr(rd), _ptr(rf), _ptr(rb),
+                                            _ptr(lengths), _ptr(starts), n_intervals, _ptr(counts_dev),
+                                            feat.shape[-1], n_vox_total, vox_per_frame, layout, _dtype_code(feat),
+                                            _ptr(ws), ws.numel(), _stream()), "bevpool_v2_forward_dense")
+
+
+def _launch_transpose(src, dst, b, c, zyx, to_channels_last):
+    lib = _lib.load()
+    _lib.check(lib.bevpool_grid_transpose(_ptr(src), _ptr(dst), b, c, zyx, 1 if to_channels_last else 0,
+                                          _dtype_code(src), _stream()), "bevpool_grid_transpose")
+
+
+def _backward_general(out_grad_cl, depth, feat, rd, rf, rb):
+    """Regroup by ranks_feat on the device (bev_pool.py:47-57), then the pixel-major kernel."""
+    lib = _lib.load()
+    n = rd.numel()
+    dev = feat.device
+    depth_grad = torch.zeros_like(depth)
+    feat_grad = torch.zeros_like(feat)
+    if n == 0:
+        return depth_grad, feat_grad
+    n_pixels = feat.numel() // feat.shape[-1]
+    bp = torch.empty((5, n), dtype=torch.int32, device=dev)     # rd, rf, rb, starts, lengths
+    n_bp = torch.empty(1, dtype=torch.int32, device=dev)
+    ws_bytes = lib.bevpool_v2_backward_regroup_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.bevpool_v2_backward_regroup(_ptr(rd), _ptr(rf), _ptr(rb), n, max(n_pixels - 1, 0),
+                                               _ptr(bp[0]), _ptr(bp[1]), _ptr(bp[2]), _ptr(bp[3]), _ptr(bp[4]),
+                                               _ptr(n_bp), _ptr(ws), ws.numel(), _stream()),
+               "bevpool_v2_backward_regroup")
+    n_intervals = int(n_bp.item())      # the reference syncs here too (torch.where, bev_pool.py:53)
+    _lib.check(lib.bevpool_v2_backward(_ptr(out_grad_cl), _ptr(depth_grad), _ptr(feat_grad), _ptr(depth), _ptr(feat),
+                                       _ptr(bp[0]), _ptr(bp[1]), _ptr(bp[2]), _ptr(bp[4]), _ptr(bp[3]),
+                                       n, n_intervals, feat.shape[-1], _dtype_code(feat), _stream()),
+               "bevpool_v2_backward")
+    return depth_grad, feat_grad
+
+
+def _backward_dense(out_grad_cl, depth, feat, plan):
+    lib = _lib.load()
+    depth_grad = torch.empty_like(depth)
+    feat_grad = torch.empty_like(feat)
+    _lib.check(lib.bevpool_v2_backward_dense(_ptr(out_grad_cl), _ptr(depth_grad), _ptr(feat_grad), _ptr(depth),
+                                             _ptr(feat), _ptr(plan.point_rank), plan.bn, plan.d, plan.hw,
+                                             feat.shape[-1], _dtype_code(feat), _stream()),
+               "bevpool_v2_backward_dense")
+    return depth_grad, feat_grad
+
+
+# ----------------------------------------------------------------------------- autograd functions
+class QuickCumsumCuda(torch.autograd.Function):
+    """Reference-contract op (bev_pool.py:11-83): returns channels-last [B, Z, Y, X, C]."""
+
+    @staticmethod
+    def forward(ctx, depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
+                interval_lengths):
+        depth, feat, rd, rf, rb, starts, lengths = _canon_inputs(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                                                                 interval_starts, interval_lengths)
+        shape = _shape5(bev_feat_shape, feat)
+        out = feat.new_zeros(shape)
+        _launch_forward(depth, feat, out, rd, rf, rb, starts, lengths)
+        ctx.save_for_backward(rb, depth, feat, rf, rd)
+        return out
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        rb, depth, feat, rf, rd = ctx.saved_tensors
+        out_grad = out_grad.contiguous().to(feat.dtype)
+        depth_grad, feat_grad = _backward_general(out_grad, depth, feat, rd, rf, rb)
+        return depth_grad, feat_grad, None, None, None, None, None, None
+
+
+class _BevPoolV2Fused(torch.autograd.Function):
+    """bev_pool_v2 as one fused pass: returns [B, C, Z, Y, X] directly."""
+
+    @staticmethod
+    def forward(ctx, depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
+                interval_lengths):
+        plan_key = (ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths)
+        in_depth_dtype, in_feat_dtype = depth.dtype, feat.dtype
+        depth, feat, rd, rf, rb, starts, lengths = _canon_inputs(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                                                                 interval_starts, interval_lengths)
+        B, Z, Y, X, C = _shape5(bev_feat_shape, feat)
+        ctx.plan = _find_plan(*plan_key, depth, feat)
+        ctx.shape = (B, Z, Y, X, C)
+        ctx.in_dtypes = (in_depth_dtype, in_feat_dtype)
+        if C % 4 != 0:
+            # odd channel counts (the reference's KAT has C=2): scalar kernel + transpose kernel
+            out_cl = feat.new_zeros((B, Z, Y, X, C))
+            _launch_forward(depth, feat, out_cl, rd, rf, rb, starts, lengths)
+            out = feat.new_empty((B, C, Z, Y, X))
+            _launch_transpose(out_cl, out, B, C, Z * Y * X, to_channels_last=False)
+        else:
+            out = feat.new_empty((B, C, Z, Y, X))
+            _launch_forward_dense(depth, feat, out, rd, rf, rb, starts, lengths, starts.numel(), None,
+                                  B * Z * Y * X, Z * Y * X, _lib.LAYOUT_BCZYX)
+        ctx.save_for_backward(rb, depth, feat, rf, rd)
+        return out
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        rb, depth, feat, rf, rd = ctx.saved_tensors
+        B, Z, Y, X, C = ctx.shape
+        out_grad = out_grad.contiguous().to(feat.dtype)
+        og_cl = out_grad.new_empty((B, Z, Y, X, C))
+        _launch_transpose(out_grad, og_cl, B, C, Z * Y * X, to_channels_last=True)
+        if ctx.plan is not None and C % 4 == 0:
+            depth_grad, feat_grad = _backward_dense(og_cl, depth, feat, ctx.plan)
+        else:
+            depth_grad, feat_grad = _backward_general(og_cl, depth, feat, rd, rf, rb)
+        return depth_grad.to(ctx.in_dtypes[0]), feat_grad.to(ctx.in_dtypes[1]), None, None, None, None, None, None
+
+
+def bev_pool_v2(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                bev_feat_shape, interval_starts, interval_lengths):
+    """Drop-in for the reference `bev_pool_v2` (bev_pool.py:86-92).
+
+    depth [B,N,D,H,W]; feat [B,N,H,W,C] (channels last); ranks_* int [P]; interval_* int [I];
+    bev_feat_shape (B,Z,Y,X,C) of ints or 0-dim tensors. Returns a new contiguous [B,C,Z,Y,X]
+    tensor, differentiable w.r.t. depth and feat.
+    """
+    return _BevPoolV2Fused.apply(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape,
+                                 interval_starts, interval_lengths)
+
+
+class TRTBEVPoolv2(torch.autograd.Function):
+    """Inference wrapper (bev_pool.py:95-142): depth [N,D,H,W], feat [N,H,W,C] -> [1,out_h,out_w,C].
+    The channels-last result is produced directly by the fused kernel (Z == 1, so
+    [B,Z,Y,X,C] IS [1,out_h,out_w,C]) instead of pool + two permutes."""
+
+    @staticmethod
+    def symbolic(g, depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths,
+                 out_height=128, out_width=128):
+        return g.op('mmdeploy::bev_pool_v2', depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,
+                    interval_lengths, out_height_i=out_height, out_width_i=out_width)
+
+    @staticmethod
+    def forward(g, depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths,
+                out_height=128, out_width=128):
+        depth, feat, rd, rf, rb, starts, lengths = _canon_inputs(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                                                                 interval_starts, interval_lengths)
+        C = feat.shape[-1]
+        if C % 4 != 0:
+            out = feat.new_zeros((1, out_height, out_width, C))
+            _launch_forward(depth, feat, out, rd, rf, rb, starts, lengths)
+            return out
+        out = feat.new_empty((1, out_height, out_width, C))
+        n_vox = out_height * out_width
+        _launch_forward_dense(depth, feat, out, rd, rf, rb, starts, lengths, starts.numel(), None, n_vox, n_vox,
+                              _lib.LAYOUT_BZYXC)
+        return out

@@ -1,0 +1,166 @@
+// Shared device/host helpers for the bevpool_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bevpool_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "bevpool_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace bevpool {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+constexpr unsigned kFullMask = 0xffffffffu;
+
+void count_launch(int n = 1);  // abi.cu
+
+inline int launch_status() {
+  cudaError_t e = cudaGetLastError();
+  return (int)e;
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// ---- cache-hinted memory ops ---------------------------------------------------------------
+// Streaming (read-once) data: do not allocate in L1 so gathered feature rows keep it.
+__device__ __forceinline__ int ldg_stream_i32(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_stream_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+// Output rows are written once and not re-read by this kernel: streaming store.
+__device__ __forceinline__ void stg_stream_f4(float4* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void stg_stream_f32(float* p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void stg_stream_u2(uint2* p, uint2 v) {
+  asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// ---- element access: 4 consecutive channels as float4, fp32 or bf16 storage ------------------
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+  // gathered (re-used) rows: default caching (L1 + L2)
+  static __device__ __forceinline__ float4 load(const float* base, int64_t elem) {
+    return __ldg(reinterpret_cast<const float4*>(base + elem));
+  }
+  static __device__ __forceinline__ float4 load_stream(const float* base, int64_t elem) {
+    return ldg_stream_f4(reinterpret_cast<const float4*>(base + elem));
+  }
+  static __device__ __forceinline__ void store(float* base, int64_t elem, float4 v) {
+    stg_stream_f4(reinterpret_cast<float4*>(base + elem), v);
+  }
+  static __device__ __forceinline__ float load1(const float* base, int64_t elem) { return __ldg(base + elem); }
+  static __device__ __forceinline__ void store1(float* base, int64_t elem, float v) { base[elem] = v; }
+};
+template <>
+struct Vec4<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 unpack(uint2 r) {
+    float4 v;
+    v.x = __uint_as_float(r.x << 16);
+    v.y = __uint_as_float(r.x & 0xffff0000u);
+    v.z = __uint_as_float(r.y << 16);
+    v.w = __uint_as_float(r.y & 0xffff0000u);
+    return v;
+  }
+  static __device__ __forceinline__ float4 load(const __nv_bfloat16* base, int64_t elem) {
+    return unpack(__ldg(reinterpret_cast<const uint2*>(base + elem)));
+  }
+  static __device__ __forceinline__ float4 load_stream(const __nv_bfloat16* base, int64_t elem) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(base + elem));
+    return unpack(r);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* base, int64_t elem, float4 v) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&lo);
+    r.y = *reinterpret_cast<uint32_t*>(&hi);
+    stg_stream_u2(reinterpret_cast<uint2*>(base + elem), r);
+  }
+  static __device__ __forceinline__ float load1(const __nv_bfloat16* base, int64_t elem) {
+    return __bfloat162float(base[elem]);
+  }
+  static __device__ __forceinline__ void store1(__nv_bfloat16* base, int64_t elem, float v) {
+    base[elem] = __float2bfloat16_rn(v);
+  }
+};
+
+__device__ __forceinline__ float4 fma4(float4 a, float s, float4 acc) {
+  acc.x = fmaf(a.x, s, acc.x);
+  acc.y = fmaf(a.y, s, acc.y);
+  acc.z = fmaf(a.z, s, acc.z);
+  acc.w = fmaf(a.w, s, acc.w);
+  return acc;
+}
+__device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  acc = fmaf(a.w, b.w, acc);
+  return acc;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+
+// ---- decoupled look-back on one 32-bit word: [31:30] flag, [29:0] value ----------------------
+constexpr uint32_t kFlagAggregate = 1u << 30;
+constexpr uint32_t kFlagPrefix = 2u << 30;
+constexpr uint32_t kValueMask = (1u << 30) - 1;
+
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// status[t * stride] belongs to tile t. Returns the exclusive prefix of `aggregate` over tiles < tile.
+// The word carries flag and value together, so no fence is required.
+__device__ __forceinline__ uint32_t lookback_exclusive(uint32_t* status, int64_t stride, int tile,
+                                                       uint32_t aggregate) {
+  if (tile == 0) {
+    st_relaxed_gpu(status, kFlagPrefix | aggregate);
+    return 0;
+  }
+  st_relaxed_gpu(status + (int64_t)tile * stride, kFlagAggregate | aggregate);
+  uint32_t excl = 0;
+  for (int t = tile - 1; t >= 0; --t) {
+    uint32_t s;
+    do {
+      s = ld_relaxed_gpu(status + (int64_t)t * stride);
+    } while ((s >> 30) == 0);
+    excl += s & kValueMask;
+    if (s & kFlagPrefix) break;
+  }
+  st_relaxed_gpu(status + (int64_t)tile * stride, kFlagPrefix | ((excl + aggregate) & kValueMask));
+  return excl;
+}
+
+}  // namespace bevpool

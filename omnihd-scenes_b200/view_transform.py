@@ -1,0 +1,260 @@
+"""Host-side mirror of the view-transform half of the reference's LSS necks
+(projects/mmdet3d_plugin/bevfusion/detectors/cam_stream_lss_bevpoolv2.py and the two
+`_depthnet` variants): grid constants, frustum, geometry, voxel_pooling_prepare_v2,
+voxel_pooling_v2 and s2c — without the conv nets around them (out of scope).
+
+    gen_dx_bx(xbound, ybound, zbound)                :77-82
+    create_frustum(final_dim, downsample, dbound)    :216-227
+    get_geometry(frustum, rots, trans)               :229-258 (callers only use the plain branch)
+    voxel_pooling_prepare_v2(coor, dx, bx, nx)       :294-351  -> (ranks_bev, ranks_depth, ranks_feat,
+                                                                  interval_starts, interval_lengths) | 5 x None
+    LSSViewTransform                                 the module-shaped shim: same method names as
+                                                     LiftSplatShoot, `frustum` kept as a Parameter so
+                                                     released checkpoints load
+
+Device work is done by csrc/prepare.cu and csrc/pool.cu through the C ABI.
+"""
+import torch
+from torch import nn
+
+from . import _lib
+from .bev_pool import bev_pool_v2, register_plan, _ptr, _stream, _launch_forward_dense, _launch_transpose, \
+    _dtype_code
+
+
+# ----------------------------------------------------------------------------- constants
+def gen_dx_bx(xbound, ybound, zbound):
+    """dx (step), bx (first voxel centre), nx (voxel counts, float divide then truncation)."""
+    rows = (xbound, ybound, zbound)
+    dx = torch.tensor([float(r[2]) for r in rows], dtype=torch.float32)
+    bx = torch.tensor([r[0] + r[2] / 2.0 for r in rows], dtype=torch.float32)
+    nx = torch.tensor([int((r[1] - r[0]) / r[2]) for r in rows], dtype=torch.int64)
+    return dx, bx, nx
+
+
+def create_frustum(final_dim, downsample, dbound):
+    """[D, fH, fW, 3] fp32 with (x_pixel, y_pixel, depth) per cell — same torch ops as the
+    reference so that the values are bit-identical to the checkpointed Parameter."""
+    ogfH, ogfW = final_dim
+    fH, fW = ogfH // downsample, ogfW // downsample
+    ds = torch.arange(*dbound, dtype=torch.float)
+    D = ds.numel()
+    xs = torch.linspace(0, ogfW - 1, fW, dtype=torch.float)
+    ys = torch.linspace(0, ogfH - 1, fH, dtype=torch.float)
+    frustum = torch.empty(D, fH, fW, 3, dtype=torch.float)
+    frustum[..., 0] = xs.view(1, 1, fW)
+    frustum[..., 1] = ys.view(1, fH, 1)
+    frustum[..., 2] = ds.view(D, 1, 1)
+    return frustum
+
+
+# ----------------------------------------------------------------------------- checks
+def _check_f32_cuda(name, t, shape_tail=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (bevpool_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32, got {t.dtype}")
+    if shape_tail is not None and tuple(t.shape[-len(shape_tail):]) != tuple(shape_tail):
+        raise ValueError(f"{name} must end with shape {tuple(shape_tail)}, got {tuple(t.shape)}")
+
+
+def _grid_struct(B, N, D, H, W, dx, bx, nx):
+    dx = torch.as_tensor(dx).detach().to("cpu", torch.float32)
+    bx = torch.as_tensor(bx).detach().to("cpu", torch.float32)
+    nx = torch.as_tensor(nx).detach().to("cpu", torch.int64)
+    lo = bx - dx / 2.            # fp32 tensor arithmetic, as cam_stream_lss_bevpoolv2.py:317
+    g = _lib.GridT()
+    g.b, g.n, g.d, g.h, g.w = B, N, D, H, W
+    for a in range(3):
+        g.nx[a] = int(nx[a])
+        g.lo[a] = float(lo[a])
+        g.dx[a] = float(dx[a])
+    return g
+
+
+# ----------------------------------------------------------------------------- geometry
+def get_geometry(frustum, rots, trans):
+    """coor [B,N,D,fH,fW,3] fp32: (x,y,z) of every frustum point in the lidar/ego frame.
+    rots/trans are img->lidar (inverse of lidar2img, bevf_faster_rcnn.py:119-128)."""
+    _check_f32_cuda("frustum", frustum, (3,))
+    _check_f32_cuda("rots", rots, (3, 3))
+    _check_f32_cuda("trans", trans, (3,))
+    if frustum.dim() != 4 or rots.dim() != 4 or trans.dim() != 3:
+        raise ValueError("expected frustum [D,H,W,3], rots [B,N,3,3], trans [B,N,3]")
+    B, N = trans.shape[:2]
+    D, H, W, _ = frustum.shape
+    frustum, rots, trans = frustum.contiguous(), rots.contiguous(), trans.contiguous()
+    coor = torch.empty((B, N, D, H, W, 3), dtype=torch.float32, device=rots.device)
+    lib = _lib.load()
+    _lib.check(lib.bevpool_geometry(_ptr(frustum), _ptr(rots), _ptr(trans), _ptr(coor), B * N, D, H * W, _stream()),
+               "bevpool_geometry")
+    return coor
+
+
+# ----------------------------------------------------------------------------- prepare
+class _Prepared:
+    """Worst-case-sized device outputs of one prepare call (no host sync yet)."""
+    __slots__ = ("rb", "rd", "rf", "starts", "lengths", "counts", "point_rank", "bn", "d", "hw", "p0")
+
+
+def _prepare_device(coor, frustum, rots, trans, B, N, D, H, W, dx, bx, nx, device):
+    lib = _lib.load()
+    g = _grid_struct(B, N, D, H, W, dx, bx, nx)
+    p0 = B * N * D * H * W
+    vtot = B * g.nx[0] * g.nx[1] * g.nx[2]
+    if p0 >= 2 ** 30 or vtot >= 2 ** 31 - 1:
+        raise ValueError("problem too large for int32 ranks: shard the frame batch")
+    out = _Prepared()
+    ranks = torch.empty((3, max(p0, 1)), dtype=torch.int32, device=device)
+    n_int = max(min(p0, vtot), 1)
+    inter = torch.empty((2, n_int), dtype=torch.int32, device=device)
+    out.rb, out.rd, out.rf = ranks[0], ranks[1], ranks[2]
+    out.starts, out.lengths = inter[0], inter[1]
+    out.counts = torch.empty(2, dtype=torch.int32, device=device)
+    out.point_rank = torch.empty(max(p0, 1), dtype=torch.int32, device=device)
+    out.bn, out.d, out.hw, out.p0 = B * N, D, H * W, p0
+    ws_bytes = lib.bevpool_prepare_v2_workspace_bytes(g)
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=device)
+    import ctypes
+    _lib.check(lib.bevpool_prepare_v2(_ptr(coor), _ptr(frustum), _ptr(rots), _ptr(trans), ctypes.byref(g),
+                                      _ptr(out.rb), _ptr(out.rd), _ptr(out.rf), _ptr(out.starts), _ptr(out.lengths),
+                                      _ptr(out.counts), _ptr(out.point_rank), _ptr(ws), ws.numel(), _stream()),
+               "bevpool_prepare_v2")
+    return out
+
+
+def voxel_pooling_prepare_v2(coor, dx, bx, nx):
+    """Free-function form of `LiftSplatShoot.voxel_pooling_prepare_v2(self, coor)`.
+
+    coor [B,N,D,H,W,3] fp32 CUDA. Returns int32 contiguous
+    (ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths) — note the order —
+    sorted by ranks_bev with ties in ascending point index, or five Nones if no point falls
+    inside the grid. Exactly one device->host read (the two counts) is performed, because the
+    API returns exact-length tensors; the reference performs at least three.
+    """
+    _check_f32_cuda("coor", coor, (3,))
+    if coor.dim() != 6:
+        raise ValueError("coor must be [B, N, D, H, W, 3]")
+    B, N, D, H, W, _ = coor.shape
+    if B * N * D * H * W == 0:
+        return None, None, None, None, None
+    coor = coor.contiguous()
+    pr = _prepare_device(coor, None, None, None, B, N, D, H, W, dx, bx, nx, coor.device)
+    P, I = (int(v) for v in pr.counts.tolist())
+    if P == 0 or I == 0:
+        return None, None, None, None, None
+    res = (pr.rb[:P], pr.rd[:P], pr.rf[:P], pr.starts[:I], pr.lengths[:I])
+    register_plan(*res, pr.point_rank, pr.bn, pr.d, pr.hw)
+    return res
+
+
+# ----------------------------------------------------------------------------- fused module path
+class _FusedViewPool(torch.autograd.Function):
+    """geometry -> rank -> sort -> pool with no host synchronisation: interval / point counts stay
+    on the device (counts_dev), buffers are worst-case sized. Backward is the sort-free kernel."""
+
+    @staticmethod
+    def forward(ctx, depth, feat_cl, prepared, shape):
+        B, Z, Y, X, C = shape
+        depth = depth.contiguous()
+        feat_cl = feat_cl.contiguous()
+        if depth.dtype != feat_cl.dtype:
+            depth, feat_cl = depth.float(), feat_cl.float()
+        out = feat_cl.new_empty((B, C, Z, Y, X))
+        _launch_forward_dense(depth, feat_cl, out, prepared.rd, prepared.rf, prepared.rb, prepared.starts,
+                              prepared.lengths, 0, prepared.counts, B * Z * Y * X, Z * Y * X, _lib.LAYOUT_BCZYX)
+        ctx.prepared, ctx.shape = prepared, shape
+        ctx.save_for_backward(depth, feat_cl)
+        return out
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        depth, feat_cl = ctx.saved_tensors
+        B, Z, Y, X, C = ctx.shape
+        pr = ctx.prepared
+        out_grad = out_grad.contiguous().to(feat_cl.dtype)
+        og_cl = out_grad.new_empty((B, Z, Y, X, C))
+        _launch_transpose(out_grad, og_cl, B, C, Z * Y * X, True)
+        depth_grad = torch.empty_like(depth)
+        feat_grad = torch.empty_like(feat_cl)
+        lib = _lib.load()
+        _lib.check(lib.bevpool_v2_backward_dense(_ptr(og_cl), _ptr(depth_grad), _ptr(feat_grad), _ptr(depth),
+                                                 _ptr(feat_cl), _ptr(pr.point_rank), pr.bn, pr.d, pr.hw, C,
+                                                 _dtype_code(feat_cl), _stream()), "bevpool_v2_backward_dense")
+        return depth_grad, feat_grad, None, None
+
+
+class LSSViewTransform(nn.Module):
+    """View-transform part of the reference's `LiftSplatShoot` (cam_stream_lss_bevpoolv2.py:149-375):
+    same attribute names (`dx`, `bx`, `nx`, `frustum`, `D`, `fH`, `fW`) and method names, no conv nets.
+    Per-axis bounds are accepted (the reference forces one scalar `grid` for x, y and z, :164-169)."""
+
+    def __init__(self, final_dim, downsample, dbound, xbound, ybound, zbound):
+        super().__init__()
+        self.final_dim = tuple(final_dim)
+        self.downsample = downsample
+        self.grid_conf = dict(xbound=list(xbound), ybound=list(ybound), zbound=list(zbound), dbound=list(dbound))
+        self.dx, self.bx, self.nx = gen_dx_bx(xbound, ybound, zbound)       # plain CPU tensors, as the reference
+        self.fH, self.fW = final_dim[0] // downsample, final_dim[1] // downsample
+        self.frustum = nn.Parameter(create_frustum(final_dim, downsample, dbound), requires_grad=False)
+        self.D = self.frustum.shape[0]
+
+    @classmethod
+    def from_config(cls, cfg):
+        return cls(cfg.final_dim, cfg.downsample, cfg.dbound, cfg.xbound, cfg.ybound, cfg.zbound)
+
+    @classmethod
+    def from_lss_args(cls, final_dim, camera_depth_range, pc_range, downsample, grid):
+        """Constructor taking the reference's own keyword set (:150)."""
+        return cls(final_dim, downsample, camera_depth_range, (pc_range[0], pc_range[3], grid),
+                   (pc_range[1], pc_range[4], grid), (pc_range[2], pc_range[5], grid))
+
+    # -- reference method names -------------------------------------------------------------
+    def get_geometry(self, rots, trans, post_rots=None, post_trans=None, extra_rots=None, extra_trans=None):
+        if any(v is not None for v in (post_rots, post_trans, extra_rots, extra_trans)):
+            # never passed by any caller in the reference; refuse rather than be silently wrong
+            raise NotImplementedError("post_/extra_ transforms are not used by the reference's callers")
+        return get_geometry(self.frustum, rots, trans)
+
+    def voxel_pooling_prepare_v2(self, coor):
+        return voxel_pooling_prepare_v2(coor, self.dx, self.bx, self.nx)
+
+    def voxel_pooling_v2(self, coor, depth, feat):
+        """coor [B,N,D,H,W,3], depth [B,N,D,H,W], feat [B,N,C,H,W] -> [B,C,Z,Y,X] (or None)."""
+        ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths = self.voxel_pooling_prepare_v2(coor)
+        if ranks_feat is None:
+            print('warning ---> no points within the predefined bev receptive field')
+            return None
+        feat = feat.permute(0, 1, 3, 4, 2).contiguous()
+        bev_feat_shape = (depth.shape[0], int(self.nx[2]), int(self.nx[1]), int(self.nx[0]), feat.shape[-1])
+        return bev_pool_v2(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
+                           interval_lengths)
+
+    @staticmethod
+    def s2c(x):
+        """[B,C,Z,Y,X] -> [B,Z*C,Y,X] (:363-365)."""
+        B, C, Z, Y, X = x.shape
+        return x.permute(0, 2, 1, 3, 4).reshape(B, Z * C, Y, X)
+
+    def get_voxels(self, depth, feat, rots, trans):
+        """Reference order of operations (:357-361) given already-computed depth / feat."""
+        return self.voxel_pooling_v2(self.get_geometry(rots, trans), depth, feat)
+
+    # -- fused path ---------------------------------------------------------------------------
+    def forward(self, depth, feat, rots, trans):
+        """Fused view transform: geometry is never materialised, nothing synchronises with the host.
+        depth [B,N,D,fH,fW], feat [B,N,C,fH,fW] -> [B,C,Z,Y,X] (all zeros if no point is in range)."""
+        _check_f32_cuda("rots", rots, (3, 3))
+        _check_f32_cuda("trans", trans, (3,))
+        B, N = trans.shape[:2]
+        D, H, W = self.D, self.fH, self.fW
+        if tuple(depth.shape) != (B, N, D, H, W):
+            raise ValueError(f"depth must be {(B, N, D, H, W)}, got {tuple(depth.shape)}")
+        C = feat.shape[2]
+        if C % 4:
+            raise ValueError("the fused path needs C % 4 == 0; use voxel_pooling_v2 for other channel counts")
+        pr = _prepare_device(None, self.frustum, rots.contiguous(), trans.contiguous(), B, N, D, H, W,
+                             self.dx, self.bx, self.nx, rots.device)
+        feat_cl = feat.permute(0, 1, 3, 4, 2).contiguous()
+        shape = (B, int(self.nx[2]), int(self.nx[1]), int(self.nx[0]), C)
+        return _FusedViewPool.apply(depth, feat_cl, pr, shape)

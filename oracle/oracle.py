@@ -1,0 +1,218 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+CPU restatement of the reference's camera->BEV hot path. Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs
+may import this module; the product package never does.
+
+Each function cites the reference lines it follows (paths relative to
+/root/reference/projects/mmdet3d_plugin):
+
+  gen_dx_bx            bevfusion/detectors/cam_stream_lss_bevpoolv2.py:77-82
+  create_frustum       same :216-227
+  get_geometry         same :229-258   (the live `else` branch :244-251 only)
+  prepare_v2           same :294-351
+  bev_pool_v2_forward  ops/bev_pool_v2/src/bev_pool_cuda.cu:21-48  (+ zeros, ops/bev_pool_v2/bev_pool.py:27)
+  bev_pool_v2_backward ops/bev_pool_v2/bev_pool.py:44-83 + src/bev_pool_cuda.cu:67-121
+  cumsum_voxel_pooling cam_stream_lss_bevpoolv2.py:85-122 (QuickCumsum) inside upstream-LSS glue
+                       — the CPU BASELINE, not a parity oracle (global cumsum loses precision)
+
+Third-party arithmetic on the path: PyTorch (`torch==1.9.1+cu111` pinned by the
+reference README:143) — trunc-toward-zero `.long()`, IEEE fp32 divide, `argsort`
+tie order. None is pinned by a reference test; this oracle is pinned instead by
+golden vectors produced by running the reference's own Python on CPU under
+torch 2.11 (tests/golden/make_golden.py) where argsort is stable, and by the
+reference's KAT (bev_pool.py:145-176).
+
+Integer work is numpy (vectorised) or C (oracle_voxel_rank); fp32 pooling is the C
+library liboracle.so built by oracle/Makefile.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            raise RuntimeError("oracle/liboracle.so missing: run `make -C oracle`")
+        _LIB = ctypes.CDLL(path)
+    return _LIB
+
+
+def _p(a, t):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+_f, _i, _l = ctypes.c_float, ctypes.c_int, ctypes.c_int64
+
+
+# --------------------------------------------------------------------------- grid / frustum
+def gen_dx_bx(xbound, ybound, zbound):
+    rows = [xbound, ybound, zbound]
+    dx = np.array([r[2] for r in rows], dtype=np.float32)
+    bx = np.array([r[0] + r[2] / 2.0 for r in rows], dtype=np.float32)
+    nx = np.array([int((r[1] - r[0]) / r[2]) for r in rows], dtype=np.int64)   # LongTensor(float) truncates
+    return dx, bx, nx
+
+
+def _linspace_f32(lo, hi, n):
+    """torch.linspace(lo, hi, n, dtype=float32) CPU semantics: step rounded to fp32, first half
+    counted up from lo, second half counted down from hi, each element a single-rounding
+    multiply-add (FMA) — reproduced here in float64 (exact product) then rounded once."""
+    lo, hi = np.float32(lo), np.float32(hi)
+    if n == 1:
+        return np.array([lo], dtype=np.float32)
+    step = np.float64(np.float32((hi - lo) / np.float32(n - 1)))
+    i = np.arange(n)
+    up = np.float64(lo) + step * i
+    down = np.float64(hi) - step * (n - 1 - i)
+    return np.where(i < n // 2, up, down).astype(np.float32)
+
+
+def create_frustum(final_dim, downsample, dbound):
+    ogfH, ogfW = final_dim
+    fH, fW = ogfH // downsample, ogfW // downsample
+    lo, hi, st = dbound
+    n = int(np.ceil((hi - lo) / st))
+    ds = (np.float32(lo) + np.arange(n, dtype=np.float32) * np.float32(st)).astype(np.float32)
+    xs = _linspace_f32(0, ogfW - 1, fW)
+    ys = _linspace_f32(0, ogfH - 1, fH)
+    fr = np.empty((n, fH, fW, 3), dtype=np.float32)
+    fr[..., 0] = xs[None, None, :]
+    fr[..., 1] = ys[None, :, None]
+    fr[..., 2] = ds[:, None, None]
+    return fr
+
+
+def get_geometry(frustum, rots, trans):
+    """coor[b,n,d,h,w,:] = rots[b,n] @ (u*d, v*d, d) + trans[b,n], every multiply and
+    add rounded separately in fp32, products summed left to right (no FMA): this is what
+    the CPU batched matmul at :250 produces bit for bit (checked against the goldens)."""
+    fr = frustum.astype(np.float32)
+    px = (fr[..., 0] * fr[..., 2]).astype(np.float32)[None, None]
+    py = (fr[..., 1] * fr[..., 2]).astype(np.float32)[None, None]
+    pz = fr[..., 2][None, None]
+    r = rots.astype(np.float32)[:, :, None, None, None]
+    t = trans.astype(np.float32)[:, :, None, None, None]
+    out = np.empty(rots.shape[:2] + fr.shape[:3] + (3,), dtype=np.float32)
+    for a in range(3):
+        acc = (r[..., a, 0] * px).astype(np.float32)
+        acc = (acc + (r[..., a, 1] * py).astype(np.float32)).astype(np.float32)
+        acc = (acc + (r[..., a, 2] * pz).astype(np.float32)).astype(np.float32)
+        out[..., a] = (acc + t[..., a]).astype(np.float32)
+    return out
+
+
+# --------------------------------------------------------------------------- prepare
+def voxel_rank(coor, dx, bx, nx):
+    """int64 rank per frustum point, -1 if outside (C loop, exact fp32 semantics)."""
+    coor = np.ascontiguousarray(coor, dtype=np.float32)
+    B = coor.shape[0]
+    n = coor.size // 3
+    dx = np.asarray(dx, dtype=np.float32)
+    bx = np.asarray(bx, dtype=np.float32)
+    lo = (bx - (dx / np.float32(2.0)).astype(np.float32)).astype(np.float32)
+    nx = np.ascontiguousarray(nx, dtype=np.int64)
+    out = np.empty(n, dtype=np.int64)
+    _lib().oracle_voxel_rank(_p(coor, _f), _l(n), _l(n // max(B, 1)), _p(lo, _f), _p(dx, _f), _p(nx, _l), _p(out, _l))
+    return out
+
+
+def prepare_v2(coor, dx, bx, nx):
+    """-> (ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths) int32,
+    or five Nones when no point is kept (:344-345)."""
+    B, N, D, H, W, _ = coor.shape
+    rank = voxel_rank(coor, dx, bx, nx)
+    kept = np.nonzero(rank >= 0)[0]
+    if kept.size == 0:
+        return None, None, None, None, None
+    ranks_depth = kept.astype(np.int64)
+    ranks_feat = (kept // (D * H * W)) * (H * W) + kept % (H * W)
+    ranks_bev = rank[kept]
+    order = np.argsort(ranks_bev, kind="stable")
+    ranks_bev, ranks_depth, ranks_feat = ranks_bev[order], ranks_depth[order], ranks_feat[order]
+    head = np.ones(ranks_bev.size, dtype=bool)
+    head[1:] = ranks_bev[1:] != ranks_bev[:-1]
+    starts = np.nonzero(head)[0]
+    lengths = np.empty_like(starts)
+    lengths[:-1] = starts[1:] - starts[:-1]
+    lengths[-1] = ranks_bev.size - starts[-1]
+    return tuple(np.ascontiguousarray(a.astype(np.int32)) for a in (ranks_bev, ranks_depth, ranks_feat, starts, lengths))
+
+
+def intervals_from_sorted(ranks):
+    head = np.ones(ranks.size, dtype=bool)
+    head[1:] = ranks[1:] != ranks[:-1]
+    starts = np.nonzero(head)[0].astype(np.int32)
+    lengths = np.diff(np.append(starts, ranks.size)).astype(np.int32)
+    return starts, lengths
+
+
+# --------------------------------------------------------------------------- pooling
+def bev_pool_v2_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape,
+                        interval_starts, interval_lengths, exact=False):
+    """out[B,Z,Y,X,C] fp32; untouched voxels stay 0 (bev_pool.py:27)."""
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    feat = np.ascontiguousarray(feat, dtype=np.float32)
+    c = feat.shape[-1]
+    out = np.zeros(tuple(int(v) for v in bev_feat_shape), dtype=np.float32)
+    args = [np.ascontiguousarray(a, dtype=np.int32) for a in
+            (ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths)]
+    _lib().oracle_bev_pool_v2_fwd(_i(c), _i(args[3].size), _p(depth, _f), _p(feat, _f),
+                                  *[_p(a, _i) for a in args], _p(out, _f), _i(1 if exact else 0))
+    return out
+
+
+def bev_pool_v2_backward(out_grad, depth, feat, ranks_depth, ranks_feat, ranks_bev, exact=False):
+    """(depth_grad like depth, feat_grad like feat); out_grad is [B,Z,Y,X,C].
+    Regroups by ranks_feat first, as QuickCumsumCuda.backward does (bev_pool.py:47-57)."""
+    out_grad = np.ascontiguousarray(out_grad, dtype=np.float32)
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    feat = np.ascontiguousarray(feat, dtype=np.float32)
+    c = feat.shape[-1]
+    order = np.argsort(np.asarray(ranks_feat), kind="stable")
+    rf = np.ascontiguousarray(np.asarray(ranks_feat)[order], dtype=np.int32)
+    rd = np.ascontiguousarray(np.asarray(ranks_depth)[order], dtype=np.int32)
+    rb = np.ascontiguousarray(np.asarray(ranks_bev)[order], dtype=np.int32)
+    starts, lengths = intervals_from_sorted(rf)
+    dg = np.zeros_like(depth)
+    fg = np.zeros_like(feat)
+    _lib().oracle_bev_pool_v2_bwd(_i(c), _i(starts.size), _p(out_grad, _f), _p(depth, _f), _p(feat, _f),
+                                  _p(rd, _i), _p(rf, _i), _p(rb, _i), _p(starts, _i), _p(lengths, _i),
+                                  _p(dg, _f), _p(fg, _f), _i(1 if exact else 0))
+    return dg, fg
+
+
+# --------------------------------------------------------------------------- CPU baseline (torch)
+def cumsum_voxel_pooling(coor, depth, feat, dx, bx, nx):
+    """The reference's PyTorch cumsum voxel-pooling path on CPU: outer product depth x feat,
+    voxelise with the reference's expression, mask, rank, argsort, then the cumsum trick
+    (x.cumsum(0); keep the last row of each rank run; first-difference) and a dense scatter
+    into [B,C,Z,Y,X]. Port of QuickCumsum.forward (:96-113) + upstream LSS voxel_pooling glue.
+    torch tensors in, torch tensor out; used only as the timed CPU baseline."""
+    import torch
+    B, N, D, H, W, _ = coor.shape
+    C = feat.shape[2]
+    x = (depth.unsqueeze(-1) * feat.permute(0, 1, 3, 4, 2).unsqueeze(2)).reshape(-1, C)
+    g = ((coor - (bx - dx / 2.)) / dx).long().view(-1, 3)
+    bidx = torch.arange(B).view(B, 1).expand(B, N * D * H * W).reshape(-1, 1)
+    g = torch.cat((g, bidx), 1)
+    kept = (g[:, 0] >= 0) & (g[:, 0] < nx[0]) & (g[:, 1] >= 0) & (g[:, 1] < nx[1]) & (g[:, 2] >= 0) & (g[:, 2] < nx[2])
+    x, g = x[kept], g[kept]
+    ranks = g[:, 3] * (nx[2] * nx[1] * nx[0]) + g[:, 2] * (nx[1] * nx[0]) + g[:, 1] * nx[0] + g[:, 0]
+    order = ranks.argsort()
+    x, g, ranks = x[order], g[order], ranks[order]
+    x = x.cumsum(0)
+    last = torch.ones(x.shape[0], dtype=torch.bool)
+    last[:-1] = ranks[1:] != ranks[:-1]
+    x, g = x[last], g[last]
+    x = torch.cat((x[:1], x[1:] - x[:-1]))
+    final = torch.zeros((B, C, int(nx[2]), int(nx[1]), int(nx[0])), dtype=x.dtype)
+    final[g[:, 3], :, g[:, 2], g[:, 1], g[:, 0]] = x
+    return final

@@ -1,0 +1,142 @@
+"""CPU: pin the oracle (oracle/) to the reference — golden vectors produced by the reference's own
+Python on CPU (tests/golden/make_golden.py) and the reference's known-answer test."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, rel_to_max
+
+
+def test_gen_dx_bx_matches_reference(orc, pkg):
+    g = np.load(os.path.join(GOLDEN, "gen_dx_bx.npz"))
+    for name, cfg in pkg.synthetic.CONFIGS.items():
+        dx, bx, nx = orc.gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound)
+        assert np.array_equal(dx, g[name + "_dx"]) and np.array_equal(bx, g[name + "_bx"])
+        assert np.array_equal(nx, g[name + "_nx"])
+        # host mirror of the product
+        tdx, tbx, tnx = pkg.gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound)
+        assert np.array_equal(tdx.numpy(), g[name + "_dx"]) and np.array_equal(tbx.numpy(), g[name + "_bx"])
+        assert np.array_equal(tnx.numpy(), g[name + "_nx"])
+
+
+def test_frustum_bit_exact(orc, pkg, golden):
+    _, g = golden
+    fr = orc.create_frustum(tuple(g["final_dim"]), int(g["downsample"]), tuple(g["dbound"]))
+    assert np.array_equal(fr, g["frustum"])
+    fr2 = pkg.create_frustum(tuple(int(v) for v in g["final_dim"]), int(g["downsample"]), tuple(float(v) for v in g["dbound"]))
+    assert np.array_equal(fr2.numpy(), g["frustum"])
+
+
+def test_geometry_bit_exact(orc, golden):
+    _, g = golden
+    coor = orc.get_geometry(g["frustum"], g["rots"], g["trans"])
+    assert coor.shape == g["coor"].shape
+    assert np.array_equal(coor, g["coor"]), f"{(coor != g['coor']).sum()} of {coor.size} coordinates differ"
+
+
+def _canon_ties(rb, rd, rf):
+    """Reorder ties into ascending point index. torch's CPU argsort (reference :336) is unstable
+    below ~5e4 elements, so on the tiny cases the reference's own tie order is arbitrary; the
+    contract (what its CUDA radix sort gives at real sizes, and what the mid_* goldens pin
+    exactly) is ascending ranks_depth inside a voxel."""
+    order = np.lexsort((rd, rb))
+    return rb[order], rd[order], rf[order]
+
+
+def test_prepare_bit_exact(orc, golden):
+    _, g = golden
+    out = orc.prepare_v2(g["coor"], g["dx"], g["bx"], g["nx"])
+    want = _canon_ties(g["ranks_bev"], g["ranks_depth"], g["ranks_feat"]) + (g["interval_starts"], g["interval_lengths"])
+    for got, ref, key in zip(out, want, ("ranks_bev", "ranks_depth", "ranks_feat", "interval_starts", "interval_lengths")):
+        assert got.dtype == np.int32
+        assert np.array_equal(got, ref), key
+
+
+@pytest.mark.parametrize("name", ["mid_bev_z1", "mid_occ_z16", "mid_omnihd", "tiny_hires"])
+def test_prepare_bit_exact_including_tie_order(orc, name):
+    """P >= 5e4: the unmodified reference's order is the stable one; everything must match as is."""
+    import hashlib
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    if "coor" in g:
+        coor = g["coor"]
+    else:
+        fr = orc.create_frustum(tuple(g["final_dim"]), int(g["downsample"]), tuple(g["dbound"]))
+        coor = orc.get_geometry(fr, g["rots"], g["trans"])
+        assert hashlib.sha256(coor.tobytes()).digest() == g["coor_sha256"].tobytes(), "geometry differs from reference"
+    out = orc.prepare_v2(coor, g["dx"], g["bx"], g["nx"])
+    for got, key in zip(out, ("ranks_bev", "ranks_depth", "ranks_feat", "interval_starts", "interval_lengths")):
+        assert np.array_equal(got, g[key]), key
+
+
+def test_prepare_empty_returns_nones(orc, golden):
+    _, g = golden
+    out = orc.prepare_v2(g["coor"] + np.float32(1e4), g["dx"], g["bx"], g["nx"])
+    assert out == (None,) * 5
+
+
+def test_truncation_keeps_minus_one_to_zero(orc):
+    # .long() truncates toward zero: a coordinate in (-1, 0) voxels lands in voxel 0 and is KEPT
+    dx = np.array([1, 1, 1], np.float32)
+    bx = np.array([0.5, 0.5, 0.5], np.float32)
+    nx = np.array([4, 4, 1], np.int64)
+    coor = np.array([[-0.5, 0.2, 0.0], [-1.0, 0.2, 0.0], [3.999, 3.5, 0.5], [4.0, 0, 0]], np.float32).reshape(1, 1, 4, 1, 1, 3)
+    r = orc.voxel_rank(coor, dx, bx, nx)
+    assert r.tolist() == [0, -1, 15, -1]
+
+
+def test_forward_matches_reference_cumsum_pool(orc, golden):
+    """The reference's own CPU cumsum pooling (QuickCumsum) on the same inputs. Tolerance 1e-4 of max:
+    the cumsum trick is the inexact party here (fp32 running sum over all P rows, then a difference;
+    SURVEY.md §8a a11) — the exact (float64) oracle shows the same 1.3e-5 gap as the fp32 one."""
+    _, g = golden
+    B = g["depth"].shape[0]
+    X, Y, Z = (int(v) for v in g["nx"])
+    feat_cl = np.ascontiguousarray(g["feat"].transpose(0, 1, 3, 4, 2))
+    C = feat_cl.shape[-1]
+    for exact in (False, True):
+        out = orc.bev_pool_v2_forward(g["depth"], feat_cl, g["ranks_depth"], g["ranks_feat"], g["ranks_bev"],
+                                      (B, Z, Y, X, C), g["interval_starts"], g["interval_lengths"], exact=exact)
+        assert rel_to_max(out.transpose(0, 4, 1, 2, 3), g["cumsum_pooled"]) <= 1e-4
+
+
+def test_reference_kat(orc):
+    """ops/bev_pool_v2/bev_pool.py:145-176."""
+    k = np.load(os.path.join(GOLDEN, "kat_bev_pool_v2.npz"))
+    starts, lengths = orc.intervals_from_sorted(k["ranks_bev"])
+    out = orc.bev_pool_v2_forward(k["depth"], k["feat"], k["ranks_depth"], k["ranks_feat"], k["ranks_bev"],
+                                  tuple(k["bev_feat_shape"]), starts, lengths)
+    assert np.isclose(out.sum(), k["loss"])
+    gd, gf = orc.bev_pool_v2_backward(np.ones_like(out), k["depth"], k["feat"], k["ranks_depth"], k["ranks_feat"],
+                                      k["ranks_bev"])
+    assert np.allclose(gd, k["grad_depth"]) and np.allclose(gf, k["grad_feat"])
+
+
+def test_backward_is_gradient_of_forward(orc, golden):
+    """Finite differences in float64 on a slice: d<out, w>/d depth and d feat."""
+    name, g = golden
+    if name != "tiny_bev_z1":
+        return
+    rng = np.random.default_rng(0)
+    B = g["depth"].shape[0]
+    X, Y, Z = (int(v) for v in g["nx"])
+    feat_cl = np.ascontiguousarray(g["feat"].transpose(0, 1, 3, 4, 2))
+    C = feat_cl.shape[-1]
+    shape = (B, Z, Y, X, C)
+    w = rng.standard_normal(shape).astype(np.float32)
+    args = (g["ranks_depth"], g["ranks_feat"], g["ranks_bev"])
+    gd, gf = orc.bev_pool_v2_backward(w, g["depth"], feat_cl, *args, exact=True)
+
+    def loss(depth, feat):
+        out = orc.bev_pool_v2_forward(depth, feat, *args, shape, g["interval_starts"], g["interval_lengths"], exact=True)
+        return float((out.astype(np.float64) * w).sum())
+
+    base = loss(g["depth"], feat_cl)
+    for idx in g["ranks_depth"][[0, 100, 5000]]:
+        d = g["depth"].copy().reshape(-1)
+        d[idx] += 0.5
+        assert abs((loss(d.reshape(g["depth"].shape), feat_cl) - base) / 0.5 - gd.reshape(-1)[idx]) < 2e-3 * max(1, abs(gd.reshape(-1)[idx]))
+    for idx in (0, 777, 20001):
+        f = feat_cl.copy().reshape(-1)
+        f[idx] += 0.5
+        assert abs((loss(g["depth"], f.reshape(feat_cl.shape)) - base) / 0.5 - gf.reshape(-1)[idx]) < 2e-3 * max(1, abs(gf.reshape(-1)[idx]))
