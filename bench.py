@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py — BEV-pool frames/s and achieved HBM GB/s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            (our arm; N>1 under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (CPU reference arm, rank 0 only)
+
+A "step" is one pass of the hot path over one batch of synthetic 6-camera frames
+(BASELINE.json configs[1]: BEVDet-R50 shapes, B=8 frames per GPU, fp32, fwd+bwd):
+frustum geometry + voxel ranking + radix sort + interval segmentation + fused
+zero-fill/pool forward + sort-free backward, through the public API
+(LSSViewTransform.forward / .backward), captured in a CUDA graph.
+
+value : whole-job frames/s, inputs resident in HBM, timed with CUDA events, max over ranks.
+e2e   : the same step fed from pinned HOST buffers (H2D of rots/trans/depth/feat/out_grad every
+        step, D2H of bev/depth_grad/feat_grad every step) inside the timed region.
+roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md §Measurement.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bev_pool_fwd_bwd_frames_per_s"
+UNIT = "frames/s"
+WORKLOAD = "bevdet_r50_b8"          # BASELINE.json configs[1]
+N_BUFFER_SETS = 4                   # rotated so no step finds its inputs in the 126 MB L2
+
+
+def algorithmic_bytes(P0, P, I, F, V, C, e=4):
+    """every input read once, every output written once at the function-level contract."""
+    idx = 4 * (2 * P) + 4 * (3 * I)
+    fwd = e * P + e * C * F + idx + e * C * V
+    bwd = e * C * V + e * P + e * C * F + idx + e * P0 + e * C * F
+    prep = 4 * (3 * P) + 4 * (2 * I)
+    return dict(fwd=fwd, bwd=bwd, prep=prep)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampled every 100 ms DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.proc.wait()
+        sm, reasons, mx = [], set(), None
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx = float(p[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_step_factory(cfg_name, frames, cams=None):
+    """The reference's CPU implementation of the path (oracle port; torch CPU ops, all host threads).
+    cams: use only the first `cams` cameras of each frame (a smaller bounded sample)."""
+    import torch
+    from __graft_entry__ import load_package
+    from oracle import oracle as orc
+    pkg = load_package()
+    cfg = pkg.synthetic.CONFIGS[cfg_name]
+    torch.set_num_threads(os.cpu_count() or 1)
+    view = pkg.LSSViewTransform.from_config(cfg)
+    rots, trans = pkg.synthetic.camera_ring(frames, cfg.n_cams, cfg.final_dim, seed=0)
+    depth, feat, gout = pkg.synthetic.pool_inputs(cfg, batch=frames, seed=0)
+    if cams is not None:
+        rots, trans, depth, feat = (t[:, :cams].contiguous() for t in (rots, trans, depth, feat))
+    fr = view.frustum.data
+
+    def step():
+        return orc.cpu_view_transform_step(fr, rots, trans, depth, feat, gout, view.dx, view.bx, view.nx)
+    return step, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames = 1.0   # bounded sample: 1 of the workload's 8 frames per step
+    step, threads = cpu_reference_step_factory(WORKLOAD, 1)
+    step()         # first call pays torch's one-off thread-pool / allocator start-up
+    t0 = time.perf_counter()
+    step()
+    t1 = time.perf_counter() - t0
+    cams = 6
+    if t1 * (args.steps + args.warmup) > 300.0:      # keep the whole run within a few minutes
+        cams = max(1, int(6 * 300.0 / (t1 * (args.steps + args.warmup))))
+        step, threads = cpu_reference_step_factory(WORKLOAD, 1, cams=cams)
+        frames = cams / 6.0
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = frames * args.steps / dt
+    sample = (f"{cams} of 6 cameras of 1 of the workload's 8 frames per step (frames are independent), "
+              "fwd+bwd incl. geometry+prepare, torch CPU ops")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": frames, "device": "cpu"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_native_arm(args):
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    lib = pkg._lib.load()          # fails loudly if the sm_100a library is missing
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = pkg.synthetic.CONFIGS[args.config]
+    B = cfg.batch if args.frames is None else args.frames     # frames per GPU (weak scaling)
+    dt_t = torch.bfloat16 if cfg.dtype == "bf16" else torch.float32
+    view = pkg.LSSViewTransform.from_config(cfg).to(dev)
+    X, Y, Z = (int(v) for v in view.nx)
+    C, D, H, W, N = cfg.channels, view.D, view.fH, view.fW, cfg.n_cams
+    V, F, P0 = B * X * Y * Z, B * N * H * W, B * N * D * H * W
+
+    # ---- buffer sets (device-resident inputs), rotated every step
+    host = []
+    for s in range(N_BUFFER_SETS):
+        rots, trans = pkg.synthetic.camera_ring(B, N, cfg.final_dim, seed=100 * rank + s)
+        depth, feat, gout = pkg.synthetic.pool_inputs(cfg, batch=B, seed=100 * rank + s)
+        host.append([t.pin_memory() for t in (rots, trans, depth.to(dt_t), feat.to(dt_t), gout.to(dt_t))])
+    sets = []
+    for h in host:
+        rots, trans, depth, feat, gout = (t.to(dev) for t in h)
+        sets.append(dict(rots=rots, trans=trans, depth=depth.requires_grad_(), feat=feat.requires_grad_(), gout=gout))
+
+    def eager_step(s):
+        s["depth"].grad = None
+        s["feat"].grad = None
+        bev = view(s["depth"], s["feat"], s["rots"], s["trans"])
+        bev.backward(s["gout"])
+        return bev
+
+    # ---- capture one CUDA graph per buffer set (whole step: ~12 kernels + 3 memsets)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for s in sets:
+            for _ in range(2):
+                eager_step(s)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    l0 = pkg._lib.launch_count()
+    eager_step(sets[0])
+    launches_per_step = pkg._lib.launch_count() - l0
+    graphs = []
+    for s in sets:
+        s["depth"].grad = None
+        s["feat"].grad = None
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            s["bev"] = view(s["depth"], s["feat"], s["rots"], s["trans"])
+            s["bev"].backward(s["gout"])
+        graphs.append(g)
+    torch.cuda.synchronize()
+
+    # measured P, I of set 0 (reported with the result; they depend on the camera ring)
+    pr = pkg.view_transform._prepare_device(None, view.frustum, sets[0]["rots"], sets[0]["trans"], B, N, D, H, W,
+                                            view.dx, view.bx, view.nx, dev)
+    P, I = (int(v) for v in pr.counts.tolist())
+    e = 2 if dt_t == torch.bfloat16 else 4
+    ab = algorithmic_bytes(P0, P, I, F, V, C, e)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- (1) device-resident throughput: graph replay, rotating buffer sets
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(lambda i: graphs[i % N_BUFFER_SETS].replay(), args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- (2) e2e: pinned host buffers -> H2D -> graph -> D2H, every step, same public API
+    out_host = [dict(bev=torch.empty((B, C, Z, Y, X), dtype=dt_t).pin_memory(),
+                     dg=torch.empty((B, N, D, H, W), dtype=dt_t).pin_memory(),
+                     fg=torch.empty((B, N, C, H, W), dtype=dt_t).pin_memory()) for _ in range(N_BUFFER_SETS)]
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    d2h = sum(t.numel() * t.element_size() for t in out_host[0].values())
+
+    def e2e_step(i):
+        k = i % N_BUFFER_SETS
+        s, h, o = sets[k], host[k], out_host[k]
+        with torch.no_grad():
+            s["rots"].copy_(h[0], non_blocking=True)
+            s["trans"].copy_(h[1], non_blocking=True)
+            s["depth"].copy_(h[2], non_blocking=True)
+            s["feat"].copy_(h[3], non_blocking=True)
+            s["gout"].copy_(h[4], non_blocking=True)
+        graphs[k].replay()
+        o["bev"].copy_(s["bev"], non_blocking=True)
+        o["dg"].copy_(s["depth"].grad, non_blocking=True)
+        o["fg"].copy_(s["feat"].grad, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 50))
+    ms_e2e = timed(e2e_step, e2e_steps, 3)
+    e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
+
+    # ---- (3) per-kernel timing for the roofline (rank 0; CUDA events on the launching stream,
+    #          L2-cold: inputs rotate over the buffer sets)
+    kernels = {}
+    if rank == 0:
+        bp = pkg.bev_pool
+        prs = [pkg.view_transform._prepare_device(None, view.frustum, s["rots"], s["trans"], B, N, D, H, W,
+                                                  view.dx, view.bx, view.nx, dev) for s in sets]
+        feat_cl = [s["feat"].detach().permute(0, 1, 3, 4, 2).contiguous() for s in sets]
+        outs = [torch.empty((B, C, Z, Y, X), dtype=dt_t, device=dev) for _ in sets]
+        tables = [bp._launch_forward_dense(s["depth"].detach(), f, o, p.rd, p.rf, p.rb, p.starts, p.lengths, 0,
+                                           p.counts, V, X * Y * Z, pkg._lib.LAYOUT_BCZYX)
+                  for s, f, o, p in zip(sets, feat_cl, outs, prs)]
+        og_cl = [torch.empty((B, Z, Y, X, C), dtype=dt_t, device=dev) for _ in sets]
+        dgs = [torch.empty_like(s["depth"]) for s in sets]
+        fgs = [torch.empty_like(f) for f in feat_cl]
+        code = bp._dtype_code(feat_cl[0])
+        st = torch.cuda.current_stream().cuda_stream
+
+        def k_fwd(i):
+            k = i % N_BUFFER_SETS
+            p = prs[k]
+            bp._launch_forward_dense(sets[k]["depth"].detach(), feat_cl[k], outs[k], p.rd, p.rf, p.rb, p.starts,
+                                     p.lengths, 0, p.counts, V, X * Y * Z, pkg._lib.LAYOUT_BCZYX, table=tables[k])
+
+        def k_tr(i):
+            k = i % N_BUFFER_SETS
+            bp._launch_transpose(sets[k]["gout"], og_cl[k], B, C, X * Y * Z, True)
+
+        def k_bwd(i):
+            k = i % N_BUFFER_SETS
+            p = prs[k]
+            lib.bevpool_v2_backward_dense(og_cl[k].data_ptr(), dgs[k].data_ptr(), fgs[k].data_ptr(),
+                                          sets[k]["depth"].data_ptr(), feat_cl[k].data_ptr(), p.point_rank.data_ptr(),
+                                          p.bn, p.d, p.hw, C, code, st)
+
+        def k_prep(i):
+            k = i % N_BUFFER_SETS
+            pkg.view_transform._prepare_device(None, view.frustum, sets[k]["rots"], sets[k]["trans"], B, N, D, H, W,
+                                               view.dx, view.bx, view.nx, dev)
+
+        reps = 40
+        for name, fn in (("pool_fwd_dense", k_fwd), ("grid_transpose", k_tr), ("pool_bwd_dense", k_bwd),
+                         ("prepare_all", k_prep)):
+            kernels[name] = timed_local(torch, fn, reps) * 1e-3      # seconds per launch
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    dom = "pool_bwd_dense" if kernels["pool_bwd_dense"] >= kernels["pool_fwd_dense"] else "pool_fwd_dense"
+    dom_bytes = ab["bwd"] if dom == "pool_bwd_dense" else ab["fwd"]
+    achieved = dom_bytes / kernels[dom] / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "frac_of_8TBps_nominal": achieved / 8000.0, "traffic": None,
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "us_per_launch": kernels[dom] * 1e6,
+                "all_kernels": {
+                    "pool_fwd_dense": {"us": kernels["pool_fwd_dense"] * 1e6, "GBps": ab["fwd"] / kernels["pool_fwd_dense"] / 1e9,
+                                       "bytes": ab["fwd"]},
+                    "pool_bwd_dense": {"us": kernels["pool_bwd_dense"] * 1e6, "GBps": ab["bwd"] / kernels["pool_bwd_dense"] / 1e9,
+                                       "bytes": ab["bwd"]},
+                    "grid_transpose(out_grad)": {"us": kernels["grid_transpose"] * 1e6,
+                                                 "GBps": 2 * e * C * V / kernels["grid_transpose"] / 1e9},
+                    "prepare(all kernels, eager launches)": {"us": kernels["prepare_all"] * 1e6, "bytes_out": ab["prep"]}},
+                "step_GBps_fwd_plus_bwd": (ab["fwd"] + ab["bwd"]) / (ms_step * 1e-3) / 1e9}
+
+    # ---- (4) CPU baseline (N=1 only): the reference's PyTorch cumsum path on this box's host cores
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        step, threads = cpu_reference_step_factory(args.config, 1)
+        step()
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 50):
+            step()
+            reps += 1
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": reps / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{reps} steps of 1 frame (of the workload's {B}), fwd+bwd incl. geometry+prepare, "
+                                  f"torch CPU ops, {dt:.1f} s"}
+
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if dt_t == torch.bfloat16 else "f32", "data": "synthetic",
+        "config": {"workload": args.config, "frames_per_gpu": B, "cams": N, "feat": [H, W], "D": D, "C": C,
+                   "grid": [X, Y, Z], "P0": P0, "P": P, "I": I,
+                   "step": "geometry+prepare+fwd+bwd (public API, one CUDA graph per buffer set)",
+                   "l2": f"inputs rotated over {N_BUFFER_SETS} buffer sets (> 126 MB L2 in total), no explicit flush",
+                   "parallelism": f"frame-sharded x{world}, no collective on the path"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches_per_step": launches_per_step,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def timed_local(torch, fn, reps):
+    for i in range(5):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        fn(5 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps      # ms per launch
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default=WORKLOAD)
+    ap.add_argument("--frames", type=int, default=None, help="frames per GPU (default: the config's batch)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_native_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -126,14 +126,17 @@ int bevpool_prepare_v2(const float* coor, const float* frustum, const float* rot
  * Forward that also zero-fills empty voxels and writes either layout directly.
  * n_intervals is read from counts_dev[1] on the device when counts_dev != NULL (no host sync),
  * else from the n_intervals argument. n_voxels_total = B*Z*Y*X, voxels_per_frame = Z*Y*X.
- * `out` need NOT be zeroed. workspace holds the strip->interval table. */
+ * `out` need NOT be zeroed. workspace holds the strip->interval table: build_table != 0 rebuilds it
+ * from the interval arrays first (one extra small launch); 0 re-uses the table a previous call with
+ * the same interval arrays left there (fixed-camera inference, per-kernel timing). */
 size_t bevpool_v2_forward_dense_workspace_bytes(int64_t n_voxels_total, int64_t voxels_per_frame);
 int bevpool_v2_forward_dense(const void* depth, const void* feat, void* out,
                              const int32_t* ranks_depth, const int32_t* ranks_feat, const int32_t* ranks_bev,
                              const int32_t* interval_lengths, const int32_t* interval_starts,
                              int64_t n_intervals, const int32_t* counts_dev,
                              int c, int64_t n_voxels_total, int64_t voxels_per_frame,
-                             int layout, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+                             int layout, int dtype, void* workspace, size_t workspace_bytes,
+                             int build_table, void* stream);
 
 /* Sort-free backward for rank arrays that came from bevpool_prepare_v2: walks the D depth
  * bins of every feature pixel through point_rank, writes EVERY element of depth_grad

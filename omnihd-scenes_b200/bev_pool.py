@@ -134,14 +134,21 @@ def _launch_forward(depth, feat, out, rd, rf, rb, starts, lengths):
 
 
 def _launch_forward_dense(depth, feat, out, rd, rf, rb, starts, lengths, n_intervals, counts_dev, n_vox_total,
-                          vox_per_frame, layout):
+                          vox_per_frame, layout, table=None):
+    """table: an int32 tensor that already holds the strip table (skips the table kernel)."""
     lib = _lib.load()
     ws_bytes = lib.bevpool_v2_forward_dense_workspace_bytes(n_vox_total, vox_per_frame)
-    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=feat.device)
+    build = 1
+    if table is not None:
+        ws, build = table, 0
+    else:
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=feat.device)
     _lib.check(lib.bevpool_v2_forward_dense(_ptr(depth), _ptr(feat), _ptr(out), _ptr(rd), _ptr(rf), _ptr(rb),
                                             _ptr(lengths), _ptr(starts), n_intervals, _ptr(counts_dev),
                                             feat.shape[-1], n_vox_total, vox_per_frame, layout, _dtype_code(feat),
-                                            _ptr(ws), ws.numel(), _stream()), "bevpool_v2_forward_dense")
+                                            _ptr(ws), ws.numel() * ws.element_size(), build, _stream()),
+               "bevpool_v2_forward_dense")
+    return ws
 
 
 def _launch_transpose(src, dst, b, c, zyx, to_channels_last):

@@ -490,11 +490,11 @@ static int backward_t(const void* og, void* dg, void* fg, const void* depth, con
 template <typename T, int LAYOUT>
 static int forward_dense_t(const void* depth, const void* feat, void* out, const int* rd, const int* rf, const int* rb,
                            const int* lengths, const int* starts, int64_t n_intervals, const int* counts_dev, int c,
-                           int64_t n_voxels_total, int64_t vpf, int* strip_first, cudaStream_t st) {
+                           int64_t n_voxels_total, int64_t vpf, int* strip_first, bool build_table, cudaStream_t st) {
   const int64_t frames = n_voxels_total / vpf;
   const int64_t spf = (vpf + kStrip - 1) / kStrip;
   const int64_t n_strips = frames * spf;
-  {
+  if (build_table) {
     int64_t blocks = counts_dev ? (int64_t)kNumSMs * 8 : (n_intervals + 1 + 255) / 256;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     if (blocks < 1) blocks = 1;
@@ -578,7 +578,7 @@ extern "C" int bevpool_v2_forward_dense(const void* depth, const void* feat, voi
                                         const int32_t* interval_lengths, const int32_t* interval_starts,
                                         int64_t n_intervals, const int32_t* counts_dev, int c, int64_t n_voxels_total,
                                         int64_t voxels_per_frame, int layout, int dtype, void* workspace,
-                                        size_t workspace_bytes, void* stream) {
+                                        size_t workspace_bytes, int build_table, void* stream) {
   if (n_intervals < 0 || n_voxels_total < 0 || voxels_per_frame <= 0 || n_voxels_total % voxels_per_frame)
     return BEVPOOL_ERR_BAD_ARG;
   if (c <= 0 || c % 4) return BEVPOOL_ERR_BAD_CHANNELS;
@@ -594,7 +594,8 @@ extern "C" int bevpool_v2_forward_dense(const void* depth, const void* feat, voi
   int* tbl = (int*)workspace;
 #define DISPATCH(T, L)                                                                                           \
   return forward_dense_t<T, L>(depth, feat, out, ranks_depth, ranks_feat, ranks_bev, interval_lengths,           \
-                               interval_starts, n_intervals, counts_dev, c, n_voxels_total, voxels_per_frame, tbl, st)
+                               interval_starts, n_intervals, counts_dev, c, n_voxels_total, voxels_per_frame, tbl,     \
+                               build_table != 0, st)
   if (dtype == BEVPOOL_F32) {
     if (layout == BEVPOOL_LAYOUT_BCZYX) DISPATCH(float, BEVPOOL_LAYOUT_BCZYX);
     DISPATCH(float, BEVPOOL_LAYOUT_BZYXC);

@@ -216,3 +216,71 @@ def cumsum_voxel_pooling(coor, depth, feat, dx, bx, nx):
     final = torch.zeros((B, C, int(nx[2]), int(nx[1]), int(nx[0])), dtype=x.dtype)
     final[g[:, 3], :, g[:, 2], g[:, 1], g[:, 0]] = x
     return final
+
+
+# --------------------------------------------------------------------------- CPU reference step (torch)
+def _quick_cumsum_function():
+    import torch
+
+    class QuickCumsumPort(torch.autograd.Function):
+        """Port of QuickCumsum (cam_stream_lss_bevpoolv2.py:96-122): cumsum over all kept points,
+        keep the last row of every rank run, first-difference; backward gathers gradx by run id."""
+
+        @staticmethod
+        def forward(ctx, x, ranks):
+            x = x.cumsum(0)
+            last = torch.ones(x.shape[0], dtype=torch.bool)
+            last[:-1] = ranks[1:] != ranks[:-1]
+            x = x[last]
+            x = torch.cat((x[:1], x[1:] - x[:-1]))
+            ctx.save_for_backward(last)
+            return x, last
+
+        @staticmethod
+        def backward(ctx, gradx, _gl):
+            (last,) = ctx.saved_tensors
+            run = torch.cumsum(last, 0)
+            run[last] -= 1
+            return gradx[run], None
+
+    return QuickCumsumPort
+
+
+def cpu_view_transform_step(frustum, rots, trans, depth, feat, out_grad, dx, bx, nx):
+    """One training-step pass of the whole path on CPU with the reference's PyTorch code shape:
+    get_geometry (:244-251) -> voxelise/mask/rank/argsort (:317-338) -> cumsum pooling (QuickCumsum,
+    :96-122) -> dense [B,C,Z,Y,X] -> backward through it (autograd) for d(depth), d(feat).
+    torch CPU tensors; returns (bev, depth_grad, feat_grad). This is what bench.py times as the
+    reference arm and the cpu_baseline — never a parity oracle."""
+    import torch
+    QC = _quick_cumsum_function()
+    B, N = trans.shape[:2]
+    D, H, W, _ = frustum.shape
+    C = feat.shape[2]
+    depth = depth.detach().requires_grad_()
+    feat = feat.detach().requires_grad_()
+    pts = frustum.repeat(B, N, 1, 1, 1, 1).unsqueeze(-1)
+    pts = torch.cat((pts[..., :2, :] * pts[..., 2:3, :], pts[..., 2:3, :]), 5)
+    coor = rots.view(B, N, 1, 1, 1, 3, 3).matmul(pts).squeeze(-1) + trans.view(B, N, 1, 1, 1, 3)
+    g = ((coor - (bx - dx / 2.)) / dx).long().view(-1, 3)
+    bidx = torch.arange(B).view(B, 1).expand(B, N * D * H * W).reshape(-1, 1)
+    g = torch.cat((g, bidx), 1)
+    kept = (g[:, 0] >= 0) & (g[:, 0] < nx[0]) & (g[:, 1] >= 0) & (g[:, 1] < nx[1]) & (g[:, 2] >= 0) & (g[:, 2] < nx[2])
+    x = (depth.unsqueeze(-1) * feat.permute(0, 1, 3, 4, 2).unsqueeze(2)).reshape(-1, C)
+    x, g = x[kept], g[kept]
+    ranks = g[:, 3] * (nx[2] * nx[1] * nx[0]) + g[:, 2] * (nx[1] * nx[0]) + g[:, 1] * nx[0] + g[:, 0]
+    order = ranks.argsort()
+    x, g, ranks = x[order], g[order], ranks[order]
+    x, last = QC.apply(x, ranks)
+    g = g[last]
+    final = _scatter_dense((B, C, int(nx[2]), int(nx[1]), int(nx[0])), g, x)
+    final.backward(out_grad)
+    return final.detach(), depth.grad, feat.grad
+
+
+def _scatter_dense(shape, g, x):
+    import torch
+    B, C, Z, Y, X = shape
+    flat = ((g[:, 3] * Z + g[:, 2]) * Y + g[:, 1]) * X + g[:, 0]              # voxel id without channel
+    out = torch.zeros((B * Z * Y * X, C), dtype=x.dtype).index_copy(0, flat, x)
+    return out.view(B, Z, Y, X, C).permute(0, 4, 1, 2, 3).contiguous()

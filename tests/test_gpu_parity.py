@@ -1,0 +1,408 @@
+"""GPU (-m gpu): parity of the sm_100a path against the oracle, the committed reference goldens
+and the reference's own CUDA kernels (oracle/_ref), all through the C-ABI library.
+
+Bars: bit-exact (np.array_equal) for ranks, sort order, intervals and geometry; fp32 forward and
+backward within 1e-5 of max|ref| (BASELINE.json north_star) — the reference-contract forward is in
+fact bit-identical; bf16 within 2^-8 of max (one output rounding, fp32 accumulation).
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, rel_to_max
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-5           # fp32, relative to max|ref|  (north_star)
+TOL_BF16 = 2.0 ** -8  # bf16 outputs
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def canon_ties(rb, rd, rf):
+    order = np.lexsort((rd, rb))
+    return rb[order], rd[order], rf[order]
+
+
+def synth_pool_case(pkg, orc, cfg, B, seed=0):
+    """Full pipeline inputs on the host + oracle prepare outputs."""
+    view = pkg.LSSViewTransform.from_config(cfg)
+    rots, trans = pkg.synthetic.camera_ring(B, cfg.n_cams, cfg.final_dim, seed=seed)
+    coor = orc.get_geometry(view.frustum.numpy(), rots.numpy(), trans.numpy())
+    ranks = orc.prepare_v2(coor, view.dx.numpy(), view.bx.numpy(), view.nx.numpy())
+    depth, feat, gout = pkg.synthetic.pool_inputs(cfg, batch=B, seed=seed)
+    return view, rots, trans, coor, ranks, depth, feat, gout
+
+
+# --------------------------------------------------------------------------------------- KAT
+def test_reference_kat_through_public_api(pkg):
+    """ops/bev_pool_v2/bev_pool.py:145-176, same inputs, same asserts."""
+    k = load("kat_bev_pool_v2")
+    depth = cu(k["depth"]).requires_grad_()
+    feat = cu(k["feat"]).requires_grad_()
+    rd, rf, rb = cu(k["ranks_depth"]), cu(k["ranks_feat"]), cu(k["ranks_bev"])
+    kept = torch.ones(rb.shape[0], device=DEV, dtype=torch.bool)
+    kept[1:] = rb[1:] != rb[:-1]
+    starts = torch.where(kept)[0].int()
+    lengths = torch.zeros_like(starts)
+    lengths[:-1] = starts[1:] - starts[:-1]
+    lengths[-1] = rb.shape[0] - starts[-1]
+    bev = pkg.bev_pool_v2(depth, feat, rd, rf, rb, (1, 1, 2, 2, 2), starts, lengths)
+    assert bev.shape == (1, 2, 1, 2, 2) and bev.is_contiguous()
+    loss = torch.sum(bev)
+    loss.backward()
+    assert loss == 4.4
+    assert depth.grad.allclose(cu(k["grad_depth"]))
+    assert feat.grad.allclose(cu(k["grad_feat"]))
+    # same through the reference-contract Function (channels-last result)
+    d2, f2 = cu(k["depth"]).requires_grad_(), cu(k["feat"]).requires_grad_()
+    out = pkg.QuickCumsumCuda.apply(d2, f2, rd, rf, rb, (1, 1, 2, 2, 2), starts, lengths)
+    assert out.shape == (1, 1, 2, 2, 2)
+    out.sum().backward()
+    assert d2.grad.allclose(cu(k["grad_depth"])) and f2.grad.allclose(cu(k["grad_feat"]))
+
+
+# --------------------------------------------------------------------------------------- geometry / prepare
+@pytest.mark.parametrize("name", ["tiny_bev_z1", "tiny_occ_z16", "tiny_omnihd", "tiny_hires"])
+def test_geometry_bit_exact_vs_reference_golden(pkg, name):
+    g = load(name)
+    coor = pkg.get_geometry(cu(g["frustum"]), cu(g["rots"]), cu(g["trans"]))
+    assert np.array_equal(coor.cpu().numpy(), g["coor"])
+
+
+@pytest.mark.parametrize("name", ["tiny_bev_z1", "tiny_occ_z16", "tiny_omnihd", "tiny_hires"])
+def test_prepare_bit_exact_vs_reference_golden(pkg, name):
+    g = load(name)
+    out = pkg.voxel_pooling_prepare_v2(cu(g["coor"]), torch.from_numpy(g["dx"]), torch.from_numpy(g["bx"]),
+                                       torch.from_numpy(g["nx"]))
+    want = canon_ties(g["ranks_bev"], g["ranks_depth"], g["ranks_feat"]) + (g["interval_starts"], g["interval_lengths"])
+    for got, ref, key in zip(out, want, ("ranks_bev", "ranks_depth", "ranks_feat", "starts", "lengths")):
+        assert got.dtype == torch.int32 and got.is_contiguous()
+        assert np.array_equal(got.cpu().numpy(), ref), key
+
+
+@pytest.mark.parametrize("name", ["mid_bev_z1", "mid_occ_z16", "mid_omnihd"])
+def test_prepare_tie_order_vs_reference_golden(pkg, orc, name):
+    """P >= 5e4: the unmodified reference's output, tie order included. Geometry comes from our own
+    kernel and must hash to the reference's coor."""
+    import hashlib
+    g = load(name)
+    fr = pkg.create_frustum(tuple(int(v) for v in g["final_dim"]), int(g["downsample"]), tuple(float(v) for v in g["dbound"]))
+    coor = pkg.get_geometry(fr.to(DEV), cu(g["rots"]), cu(g["trans"]))
+    assert hashlib.sha256(coor.cpu().numpy().tobytes()).digest() == g["coor_sha256"].tobytes()
+    out = pkg.voxel_pooling_prepare_v2(coor, torch.from_numpy(g["dx"]), torch.from_numpy(g["bx"]), torch.from_numpy(g["nx"]))
+    for got, key in zip(out, ("ranks_bev", "ranks_depth", "ranks_feat", "interval_starts", "interval_lengths")):
+        assert np.array_equal(got.cpu().numpy(), g[key]), key
+
+
+def test_prepare_none_when_nothing_in_range(pkg):
+    g = load("tiny_bev_z1")
+    out = pkg.voxel_pooling_prepare_v2(cu(g["coor"] + np.float32(1e4)), torch.from_numpy(g["dx"]),
+                                       torch.from_numpy(g["bx"]), torch.from_numpy(g["nx"]))
+    assert out == (None,) * 5
+    empty = torch.zeros((0, 6, 59, 4, 11, 3), device=DEV)
+    assert pkg.voxel_pooling_prepare_v2(empty, torch.from_numpy(g["dx"]), torch.from_numpy(g["bx"]),
+                                        torch.from_numpy(g["nx"])) == (None,) * 5
+
+
+def test_prepare_truncation_nan_inf(pkg, orc):
+    dx = torch.tensor([1., 1., 1.])
+    bx = torch.tensor([.5, .5, .5])
+    nx = torch.tensor([4, 4, 1])
+    pts = np.array([[-0.5, 0.2, 0.0], [-1.0, 0.2, 0.0], [3.999, 3.5, 0.5], [4.0, 0, 0], [np.nan, 0, 0],
+                    [np.inf, 0, 0], [1e30, 1, 0], [2.5, 2.5, 0.99]], np.float32).reshape(1, 1, 8, 1, 1, 3)
+    rb, rd, rf, st, ln = pkg.voxel_pooling_prepare_v2(cu(pts), dx, bx, nx)
+    assert rd.tolist() == [0, 7, 2] and rb.tolist() == [0, 10, 15] and rf.tolist() == [0, 0, 0]
+    assert st.tolist() == [0, 1, 2] and ln.tolist() == [1, 1, 1]
+    want = orc.prepare_v2(pts[:, :, [0, 1, 2, 3, 7]], dx.numpy(), bx.numpy(), nx.numpy())     # finite subset on the CPU
+    assert want[0].tolist() == [0, 10, 15]
+
+
+@pytest.mark.parametrize("cfg_name,B", [("bevdet_r50_b8", 8), ("occ_200x200x16_b64", 3), ("bevdepth_hires_b16", 2)])
+def test_prepare_full_size_vs_oracle(pkg, orc, cfg_name, B):
+    """BASELINE.json sizes (frame count bounded so the numpy oracle stays in seconds): bit-exact against
+    the oracle, both from materialised coor and with the geometry fused."""
+    cfg = pkg.synthetic.CONFIGS[cfg_name]
+    view, rots, trans, coor, want, *_ = synth_pool_case(pkg, orc, cfg, B)
+    view = view.to(DEV)
+    got_coor = view.get_geometry(rots.to(DEV), trans.to(DEV))
+    assert np.array_equal(got_coor.cpu().numpy(), coor)
+    got = view.voxel_pooling_prepare_v2(got_coor)
+    for a, b in zip(got, want):
+        assert np.array_equal(a.cpu().numpy(), b)
+    # fused geometry (coor never materialised)
+    from importlib import import_module
+    vt = pkg.view_transform
+    pr = vt._prepare_device(None, view.frustum, rots.to(DEV), trans.to(DEV), B, cfg.n_cams, view.D, view.fH, view.fW,
+                            view.dx, view.bx, view.nx, torch.device(DEV))
+    P, I = pr.counts.tolist()
+    assert (P, I) == (want[0].size, want[3].size)
+    for a, b in zip((pr.rb[:P], pr.rd[:P], pr.rf[:P], pr.starts[:I], pr.lengths[:I]), want):
+        assert np.array_equal(a.cpu().numpy(), b)
+    # inverse table: voxel rank of every frustum point, -1 when dropped
+    rank = orc.voxel_rank(coor, view.dx.numpy(), view.bx.numpy(), view.nx.numpy())
+    assert np.array_equal(pr.point_rank.cpu().numpy().astype(np.int64), rank)
+
+
+def test_prepare_properties_omnihd_shape(pkg):
+    """OmniHD shape (cfg 4), 2 frames, 23 M frustum points: size-independent properties."""
+    cfg = pkg.synthetic.CONFIGS["rcfusion_omnihd_b32"]
+    B = 2
+    view = pkg.LSSViewTransform.from_config(cfg).to(DEV)
+    rots, trans = pkg.synthetic.camera_ring(B, 6, cfg.final_dim, seed=5)
+    coor = view.get_geometry(rots.to(DEV), trans.to(DEV))
+    rb, rd, rf, st, ln = view.voxel_pooling_prepare_v2(coor)
+    P, I = rb.numel(), st.numel()
+    V = int(view.nx.prod())
+    assert 0 < I <= P < coor.numel() // 3
+    assert bool((rb[1:] >= rb[:-1]).all()) and int(rb.min()) >= 0 and int(rb.max()) < B * V       # sortedness
+    assert bool(((rd[1:] > rd[:-1]) | (rb[1:] != rb[:-1])).all())                                 # stable ties
+    assert torch.unique(rd).numel() == P                                                          # a permutation of kept points
+    assert int(ln.sum()) == P and int(st[0]) == 0 and bool((st[1:] == st[:-1] + ln[:-1]).all())     # intervals partition
+    assert torch.unique(rb).numel() == I and bool((rb[st.long()][1:] > rb[st.long()][:-1]).all())
+    dhw, hw = view.D * view.fH * view.fW, view.fH * view.fW
+    assert torch.equal(rf, (rd // dhw) * hw + rd % hw)
+    # recompute the voxel of every kept point with torch ops on the device (reference expression)
+    lo = (view.bx - view.dx / 2.).to(DEV)
+    vox = ((coor.view(-1, 3)[rd.long()] - lo) / view.dx.to(DEV)).long()
+    frame = rd.long() // (coor.numel() // 3 // B)
+    nx = view.nx.to(DEV)
+    assert torch.equal(rb.long(), frame * V + vox[:, 2] * nx[1] * nx[0] + vox[:, 1] * nx[0] + vox[:, 0])
+    # idempotence
+    again = view.voxel_pooling_prepare_v2(coor)
+    assert all(torch.equal(a, b) for a, b in zip((rb, rd, rf, st, ln), again))
+
+
+# --------------------------------------------------------------------------------------- forward
+def _forward_cases(pkg, orc, name_or_cfg, B=None, C=None, seed=0):
+    if isinstance(name_or_cfg, str) and name_or_cfg.startswith(("tiny", "mid")):
+        g = load(name_or_cfg)
+        feat_cl = np.ascontiguousarray(g["feat"].transpose(0, 1, 3, 4, 2))
+        X, Y, Z = (int(v) for v in g["nx"])
+        ranks = canon_ties(g["ranks_bev"], g["ranks_depth"], g["ranks_feat"]) + (g["interval_starts"], g["interval_lengths"])
+        return g["depth"], feat_cl, ranks, (g["depth"].shape[0], Z, Y, X, feat_cl.shape[-1])
+    cfg = pkg.synthetic.CONFIGS[name_or_cfg]
+    view, rots, trans, coor, ranks, depth, feat, gout = synth_pool_case(pkg, orc, cfg, B, seed)
+    if C is not None:
+        feat = torch.randn(B, cfg.n_cams, C, cfg.fH, cfg.fW, generator=torch.Generator().manual_seed(seed))
+    X, Y, Z = (int(v) for v in view.nx)
+    feat_cl = feat.permute(0, 1, 3, 4, 2).contiguous().numpy()
+    return depth.numpy(), feat_cl, ranks, (B, Z, Y, X, feat_cl.shape[-1])
+
+
+@pytest.mark.parametrize("case", ["tiny_bev_z1", "tiny_occ_z16", "tiny_omnihd", "tiny_hires",
+                                  ("bevdet_r50_b8", 2, None), ("bevdet_r50_b8", 1, 256), ("bevdet_r50_b8", 1, 4),
+                                  ("bevdet_r50_b8", 1, 6), ("bevdepth_hires_b16", 1, None)])
+def test_forward_vs_oracle_all_paths(pkg, orc, case):
+    args = (case,) if isinstance(case, str) else case
+    depth, feat_cl, (rb, rd, rf, st, ln), shape = _forward_cases(pkg, orc, *args)
+    ref = orc.bev_pool_v2_forward(depth, feat_cl, rd, rf, rb, shape, st, ln)
+    exact = orc.bev_pool_v2_forward(depth, feat_cl, rd, rf, rb, shape, st, ln, exact=True)
+    t = [cu(a) for a in (depth, feat_cl, rd, rf, rb)] + [shape, cu(st), cu(ln)]
+    # reference-contract kernel: same summation order and FMA as the reference -> bit-identical
+    out = pkg.QuickCumsumCuda.apply(*t).cpu().numpy()
+    assert out.shape == tuple(shape)
+    assert np.array_equal(out, ref)
+    assert rel_to_max(out, exact) <= TOL
+    # fused dense kernel writing [B,C,Z,Y,X] (zero fill + pool + layout in one pass)
+    bev = pkg.bev_pool_v2(*t)
+    assert bev.shape == (shape[0], shape[4], shape[1], shape[2], shape[3]) and bev.is_contiguous()
+    assert rel_to_max(bev.permute(0, 2, 3, 4, 1).cpu().numpy(), exact) <= TOL
+    if shape[1] == 1:
+        trt = pkg.TRTBEVPoolv2.apply(t[0][0], t[1][0], t[2], t[3], t[4], t[6], t[7], shape[2], shape[3]) \
+            if shape[0] == 1 else None
+        if trt is not None:
+            assert trt.shape == (1, shape[2], shape[3], shape[4])
+            assert rel_to_max(trt.cpu().numpy()[0], exact[0, 0]) <= TOL
+
+
+def test_forward_long_intervals_and_garbage_output_buffer(pkg, orc):
+    """Hand-built ranks: one interval of 5000 points, one of 97, many of 1; arbitrary (non-prepare)
+    rank arrays; the dense kernel must overwrite a poisoned output completely."""
+    rng = np.random.default_rng(3)
+    n_feat, n_depth, C = 300, 9000, 64
+    B, Z, Y, X = 2, 2, 5, 13          # 130 voxels per frame: partial last strip
+    lens = np.array([5000, 97, 1, 1, 33, 96, 300, 1, 2, 64, 7], dtype=np.int32)
+    vox = np.sort(rng.choice(B * Z * Y * X, size=lens.size, replace=False)).astype(np.int32)
+    rb = np.repeat(vox, lens).astype(np.int32)
+    P = rb.size
+    rd = rng.integers(0, n_depth, P).astype(np.int32)
+    rf = rng.integers(0, n_feat, P).astype(np.int32)
+    st = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    depth = rng.random(n_depth, dtype=np.float32).reshape(1, 1, n_depth, 1, 1)
+    feat = rng.standard_normal((1, 1, n_feat, 1, C), dtype=np.float32)
+    shape = (B, Z, Y, X, C)
+    exact = orc.bev_pool_v2_forward(depth, feat, rd, rf, rb, shape, st, lens, exact=True)
+    t = [cu(a) for a in (depth, feat, rd, rf, rb)] + [shape, cu(st), cu(lens)]
+    assert rel_to_max(pkg.QuickCumsumCuda.apply(*t).cpu().numpy(), exact) <= TOL
+    junk = torch.full((B * C * Z * Y * X + 1024,), float("nan"), device=DEV)      # poison the allocator's next block
+    del junk
+    bev = pkg.bev_pool_v2(*t)
+    assert torch.isfinite(bev).all()
+    assert rel_to_max(bev.permute(0, 2, 3, 4, 1).cpu().numpy(), exact) <= TOL
+    assert int((bev != 0).any(dim=1).sum()) == lens.size
+
+
+def test_forward_matches_reference_cuda_kernel_bitwise(pkg, orc):
+    """The reference's unmodified bev_pool_cuda.cu compiled for sm_100a (oracle/_ref) on the same inputs."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_bevpool_v2.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built (reference tree absent at build time)")
+    ref = ctypes.CDLL(path)
+    depth, feat_cl, (rb, rd, rf, st, ln), shape = _forward_cases(pkg, orc, "bevdet_r50_b8", 2)
+    t = [cu(a) for a in (depth, feat_cl, rd, rf, rb, st, ln)]
+    out_ref = torch.zeros(shape, device=DEV)
+    torch.cuda.synchronize()
+    p = lambda x: ctypes.c_void_p(x.data_ptr())
+    rc = ref.ref_bev_pool_v2_fwd(shape[4], st.size, p(t[0]), p(t[1]), p(t[2]), p(t[3]), p(t[4]), p(t[5]), p(t[6]), p(out_ref))
+    torch.cuda.synchronize()
+    assert rc == 0
+    out = pkg.QuickCumsumCuda.apply(t[0], t[1], t[2], t[3], t[4], shape, t[5], t[6])
+    assert torch.equal(out, out_ref)
+    # and the backward, regrouped on the host the way bev_pool.py:47-57 does
+    gout = torch.randn(shape, device=DEV)
+    order = t[3].argsort(stable=True)
+    rf_s, rd_s, rb_s = t[3][order].contiguous(), t[2][order].contiguous(), t[4][order].contiguous()
+    kept = torch.ones(rf_s.numel(), dtype=torch.bool, device=DEV)
+    kept[1:] = rf_s[1:] != rf_s[:-1]
+    st_bp = torch.where(kept)[0].int()
+    ln_bp = torch.diff(torch.cat([st_bp, torch.tensor([rf_s.numel()], device=DEV, dtype=torch.int32)])).int()
+    dg_ref, fg_ref = torch.zeros_like(t[0]), torch.zeros_like(t[1])
+    torch.cuda.synchronize()
+    rc = ref.ref_bev_pool_v2_bwd(shape[4], st_bp.numel(), p(gout), p(t[0]), p(t[1]), p(rd_s), p(rf_s), p(rb_s), p(st_bp),
+                                 p(ln_bp), p(dg_ref), p(fg_ref))
+    torch.cuda.synchronize()
+    assert rc == 0
+    d = t[0].clone().requires_grad_()
+    f = t[1].clone().requires_grad_()
+    pkg.QuickCumsumCuda.apply(d, f, t[2], t[3], t[4], shape, t[5], t[6]).backward(gout)
+    assert rel_to_max(d.grad.cpu().numpy(), dg_ref.cpu().numpy()) <= TOL
+    assert rel_to_max(f.grad.cpu().numpy(), fg_ref.cpu().numpy()) <= TOL
+
+
+# --------------------------------------------------------------------------------------- backward
+@pytest.mark.parametrize("case", ["tiny_bev_z1", "tiny_occ_z16", ("bevdet_r50_b8", 2, None), ("bevdet_r50_b8", 1, 256),
+                                  ("bevdet_r50_b8", 1, 6)])
+def test_backward_general_path_vs_oracle(pkg, orc, case):
+    """Arbitrary rank tensors (no plan attached): device regroup by ranks_feat + pixel-major kernel."""
+    args = (case,) if isinstance(case, str) else case
+    depth, feat_cl, (rb, rd, rf, st, ln), shape = _forward_cases(pkg, orc, *args)
+    rng = np.random.default_rng(1)
+    gout_cl = rng.standard_normal(shape).astype(np.float32)
+    gd, gf = orc.bev_pool_v2_backward(gout_cl, depth, feat_cl, rd, rf, rb, exact=True)
+    for fn, g in ((pkg.QuickCumsumCuda.apply, cu(gout_cl)),
+                  (pkg.bev_pool_v2, cu(gout_cl).permute(0, 4, 1, 2, 3).contiguous())):
+        d, f = cu(depth).requires_grad_(), cu(feat_cl).requires_grad_()
+        out = fn(d, f, cu(rd), cu(rf), cu(rb), shape, cu(st), cu(ln))
+        out.backward(g)
+        assert rel_to_max(d.grad.cpu().numpy(), gd) <= TOL
+        assert rel_to_max(f.grad.cpu().numpy(), gf) <= TOL
+
+
+@pytest.mark.parametrize("cfg_name,B", [("bevdet_r50_b8", 8), ("occ_200x200x16_b64", 2), ("bevdepth_hires_b16", 1)])
+def test_view_transform_fwd_bwd_vs_oracle(pkg, orc, cfg_name, B):
+    """Public API end to end at BASELINE sizes: get_geometry -> voxel_pooling_v2 (prepare + bev_pool_v2 with
+    the sort-free backward) and the fully fused module forward; both against the float64 oracle."""
+    cfg = pkg.synthetic.CONFIGS[cfg_name]
+    view, rots, trans, coor, (rb, rd, rf, st, ln), depth, feat, gout = synth_pool_case(pkg, orc, cfg, B)
+    X, Y, Z = (int(v) for v in view.nx)
+    C = cfg.channels
+    feat_cl = feat.permute(0, 1, 3, 4, 2).contiguous().numpy()
+    ref = orc.bev_pool_v2_forward(depth.numpy(), feat_cl, rd, rf, rb, (B, Z, Y, X, C), st, ln, exact=True)
+    gd, gf = orc.bev_pool_v2_backward(gout.permute(0, 2, 3, 4, 1).contiguous().numpy(), depth.numpy(), feat_cl,
+                                      rd, rf, rb, exact=True)
+    view = view.to(DEV)
+    for mode in ("api", "fused"):
+        d = depth.to(DEV).requires_grad_()
+        f = feat.to(DEV).requires_grad_()
+        if mode == "api":
+            bev = view.voxel_pooling_v2(view.get_geometry(rots.to(DEV), trans.to(DEV)), d, f)
+        else:
+            bev = view(d, f, rots.to(DEV), trans.to(DEV))
+        assert bev.shape == (B, C, Z, Y, X)
+        assert rel_to_max(bev.detach().permute(0, 2, 3, 4, 1).cpu().numpy(), ref) <= TOL, mode
+        bev.backward(gout.to(DEV))
+        assert rel_to_max(d.grad.cpu().numpy(), gd) <= TOL, mode
+        assert rel_to_max(f.grad.permute(0, 1, 3, 4, 2).cpu().numpy(), gf) <= TOL, mode
+        # dropped points get exactly zero depth gradient
+        rank = orc.voxel_rank(coor, view.dx.numpy(), view.bx.numpy(), view.nx.numpy())
+        assert float(d.grad.reshape(-1)[torch.from_numpy(rank < 0).to(DEV)].abs().max()) == 0.0
+
+
+def test_linearity_and_checksum_full_size(pkg):
+    """cfg 2 full size, no oracle: pool(a*d1 + d2, f) == a*pool(d1,f) + pool(d2,f); sum over the grid equals
+    the sum over kept points of depth * sum_c feat (a checksum of checksums)."""
+    cfg = pkg.synthetic.CONFIGS["bevdet_r50_b8"]
+    B = cfg.batch
+    view = pkg.LSSViewTransform.from_config(cfg).to(DEV)
+    rots, trans = pkg.synthetic.camera_ring(B, 6, cfg.final_dim, seed=11)
+    depth, feat, _ = pkg.synthetic.pool_inputs(cfg, seed=11)
+    d1, f = depth.to(DEV), feat.to(DEV)
+    d2 = torch.rand_like(d1)
+    coor = view.get_geometry(rots.to(DEV), trans.to(DEV))
+    p1 = view.voxel_pooling_v2(coor, d1, f)
+    p2 = view.voxel_pooling_v2(coor, d2, f)
+    p3 = view.voxel_pooling_v2(coor, 0.5 * d1 + d2, f)
+    assert rel_to_max((0.5 * p1 + p2).cpu().numpy(), p3.cpu().numpy()) <= TOL
+    rb, rd, rf, st, ln = view.voxel_pooling_prepare_v2(coor)
+    f_cl = f.permute(0, 1, 3, 4, 2).reshape(-1, cfg.channels)
+    want = (d1.reshape(-1)[rd.long()].double() * f_cl.double().sum(1)[rf.long()]).sum()
+    got = p1.double().sum()
+    assert abs(float(got - want)) <= 1e-6 * float((d1.reshape(-1)[rd.long()].double() * f_cl.double().abs().sum(1)[rf.long()]).sum())
+
+
+def test_bf16_io(pkg, orc):
+    """bf16 in / bf16 out (explicit extension): compared with the fp32 oracle fed the bf16-rounded inputs."""
+    depth, feat_cl, (rb, rd, rf, st, ln), shape = _forward_cases(pkg, orc, "bevdet_r50_b8", 2)
+    d16, f16 = cu(depth).bfloat16(), cu(feat_cl).bfloat16()
+    dq, fq = d16.float().cpu().numpy(), f16.float().cpu().numpy()
+    ref = orc.bev_pool_v2_forward(dq, fq, rd, rf, rb, shape, st, ln, exact=True)
+    rng = np.random.default_rng(2)
+    g16 = cu(rng.standard_normal((shape[0], shape[4]) + tuple(shape[1:4])).astype(np.float32)).bfloat16()
+    gq = g16.float().permute(0, 2, 3, 4, 1).contiguous().cpu().numpy()
+    gd, gf = orc.bev_pool_v2_backward(gq, dq, fq, rd, rf, rb, exact=True)
+    d = d16.clone().requires_grad_()
+    f = f16.clone().requires_grad_()
+    bev = pkg.bev_pool_v2(d, f, cu(rd), cu(rf), cu(rb), shape, cu(st), cu(ln))
+    assert bev.dtype == torch.bfloat16
+    assert rel_to_max(bev.float().permute(0, 2, 3, 4, 1).cpu().numpy(), ref) <= TOL_BF16
+    bev.backward(g16)
+    assert d.grad.dtype == torch.bfloat16 and f.grad.dtype == torch.bfloat16
+    assert rel_to_max(d.grad.float().cpu().numpy(), gd) <= TOL_BF16
+    assert rel_to_max(f.grad.float().cpu().numpy(), gf) <= TOL_BF16
+
+
+def test_grid_transpose_roundtrip(pkg):
+    x = torch.randn(3, 80, 2, 7, 45, device=DEV)
+    cl = torch.empty(3, 2, 7, 45, 80, device=DEV)
+    pkg.bev_pool._launch_transpose(x, cl, 3, 80, 2 * 7 * 45, True)
+    assert torch.equal(cl, x.permute(0, 2, 3, 4, 1).contiguous())
+    back = torch.empty_like(x)
+    pkg.bev_pool._launch_transpose(cl, back, 3, 80, 2 * 7 * 45, False)
+    assert torch.equal(back, x)
+
+
+def test_errors_are_loud(pkg):
+    g = load("tiny_bev_z1")
+    d, f = cu(g["depth"]), cu(np.ascontiguousarray(g["feat"].transpose(0, 1, 3, 4, 2)))
+    rb, rd, rf, st, ln = (cu(g[k]) for k in ("ranks_bev", "ranks_depth", "ranks_feat", "interval_starts", "interval_lengths"))
+    with pytest.raises(ValueError):
+        pkg.bev_pool_v2(d, f, rd, rf[:-1], rb, (2, 1, 128, 128, 8), st, ln)
+    with pytest.raises(ValueError):
+        pkg.bev_pool_v2(d, f, rd, rf, rb, (2, 1, 128, 128, 16), st, ln)
+    with pytest.raises(ValueError):
+        pkg.bev_pool_v2(d, f, rd, rf, rb.cpu(), (2, 1, 128, 128, 8), st, ln)
+    lib = pkg._lib.load()
+    assert lib.bevpool_v2_forward(0, 0, 0, 0, 0, 0, 0, 0, 5, 5, 8, 0, 0) == -1
+    assert lib.bevpool_v2_forward(0, 0, 0, 0, 0, 0, 0, 0, 5, 5, 0, 0, 0) == -2
+    assert lib.bevpool_v2_forward_dense(1, 1, 1, 1, 1, 1, 1, 1, 5, 0, 8, 64, 64, 1, 0, 1, 4, 1, 0) == -3

@@ -1,0 +1,154 @@
+"""CPU (-m "not gpu"): the C-ABI library loads and exports every declared symbol (no compute
+calls), host-side logic of the plugin mirror, frame sharding over gloo with world_size 2."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    header = open(os.path.join(ROOT, "include", "bevpool_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(bevpool_\w+)\s*\(", header))
+    assert len(declared) >= 14
+    lib = pkg._lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/bevpool_b200.h but not exported"
+    assert declared == set(pkg._lib.SIGNATURES), "ctypes signature table out of sync with the header"
+    assert lib.bevpool_b200_abi_version() == 1
+    assert lib.bevpool_b200_strerror(-3).decode() == "workspace too small"
+
+
+def test_library_is_in_tree_and_sm100a_only(pkg):
+    path = pkg._lib.library_path()
+    assert path.startswith(ROOT) and os.path.exists(path)
+    assert "compute_100a" in " ".join(pkg.build.FLAGS) and "-use_fast_math" not in pkg.build.FLAGS
+
+
+def test_product_never_imports_oracle():
+    pkg_dir = os.path.join(ROOT, "omnihd-scenes_b200")
+    for fn in os.listdir(pkg_dir):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg_dir, fn)).read()
+            assert "oracle" not in src.replace("no oracle", ""), f"{fn} mentions the oracle"
+
+
+def test_no_cpu_fallback(pkg):
+    d = torch.rand(1, 1, 2, 2, 2)
+    f = torch.ones(1, 1, 2, 2, 2)
+    i = torch.zeros(4, dtype=torch.int32)
+    with pytest.raises(ValueError, match="CUDA"):
+        pkg.bev_pool_v2(d, f, i, i, i, (1, 1, 2, 2, 2), i[:1], i[:1])
+    with pytest.raises(ValueError, match="CUDA"):
+        pkg.voxel_pooling_prepare_v2(torch.zeros(1, 1, 2, 2, 2, 3), *pkg.gen_dx_bx((0, 4, 1), (0, 4, 1), (0, 1, 1)))
+    with pytest.raises(ValueError, match="CUDA"):
+        pkg.get_geometry(torch.zeros(2, 2, 2, 3), torch.zeros(1, 1, 3, 3), torch.zeros(1, 1, 3))
+
+
+def test_view_transform_module_state(pkg):
+    cfg = pkg.synthetic.CONFIGS["rcfusion_omnihd_b32"]
+    v = pkg.LSSViewTransform.from_config(cfg)
+    # frustum must stay in the state_dict with the reference's shape (checkpoint compatibility)
+    sd = v.state_dict()
+    assert list(sd) == ["frustum"] and tuple(sd["frustum"].shape) == (59, 136, 240, 3)
+    assert v.nx.tolist() == [240, 160, 16] and v.D == 59 and (v.fH, v.fW) == (136, 240)
+    v2 = pkg.LSSViewTransform.from_lss_args((544, 960), [1, 60, 1], [-60, -40, -3, 60, 40, 5], 4, 0.5)
+    assert torch.equal(v2.frustum, v.frustum) and torch.equal(v2.bx, v.bx)
+    x = torch.arange(2 * 3 * 4 * 5 * 6, dtype=torch.float32).view(2, 3, 4, 5, 6)
+    assert torch.equal(pkg.LSSViewTransform.s2c(x), torch.cat(x.unbind(dim=2), 1))
+    with pytest.raises(NotImplementedError):
+        v.get_geometry(torch.zeros(1, 6, 3, 3), torch.zeros(1, 6, 3), post_rots=torch.zeros(1))
+
+
+def test_config_shapes_match_survey(pkg):
+    c = pkg.synthetic.CONFIGS
+    assert (c["bevdet_r50_b8"].D, c["bevdet_r50_b8"].fH, c["bevdet_r50_b8"].fW) == (59, 16, 44)
+    assert (c["bevdepth_hires_b16"].D, c["bevdepth_hires_b16"].fH, c["bevdepth_hires_b16"].fW) == (118, 32, 88)
+    assert c["occ_200x200x16_b64"].D == 88
+    rots, trans = pkg.synthetic.camera_ring(2, 6, (256, 704), seed=0)
+    assert rots.shape == (2, 6, 3, 3) and trans.shape == (2, 6, 3) and rots.dtype == torch.float32
+    r2, _ = pkg.synthetic.camera_ring(2, 6, (256, 704), seed=0)
+    assert torch.equal(rots, r2)
+
+
+def test_plugin_install_registers_reference_module_path(pkg):
+    mod = pkg.plugin.install(force=True)
+    import importlib
+    m = importlib.import_module("projects.mmdet3d_plugin.ops.bev_pool_v2.bev_pool")
+    assert m is mod and m.bev_pool_v2 is pkg.bev_pool_v2 and m.__all__ == ['bev_pool_v2', 'TRTBEVPoolv2']
+
+    class FakeLSS:
+        def get_geometry(self, *a, **k):
+            return "orig"
+
+        def voxel_pooling_prepare_v2(self, coor):
+            return "orig"
+    pkg.plugin.patch_lss_class(FakeLSS)
+    assert FakeLSS._bevpool_b200_orig_prepare is not FakeLSS.voxel_pooling_prepare_v2
+    # non-default transforms still go to the original implementation
+    assert FakeLSS().get_geometry(None, None, post_rots=1) == "orig"
+    del sys.modules["projects.mmdet3d_plugin.ops.bev_pool_v2.bev_pool"]
+
+
+def test_plan_registry_is_identity_and_version_checked(pkg):
+    bp = pkg.bev_pool
+    t = [torch.zeros(4, dtype=torch.int32) for _ in range(5)]
+    bp.register_plan(*t, point_rank=torch.zeros(8, dtype=torch.int32), bn=1, d=2, hw=4)
+    depth, feat = torch.zeros(8), torch.zeros(4, 3)
+    assert bp._find_plan(*t, depth, feat) is not None
+    assert bp._find_plan(t[0], t[1].clone(), t[2], t[3], t[4], depth, feat) is None      # different object
+    t[1].add_(1)                                                                         # mutated in place
+    assert bp._find_plan(*t, depth, feat) is None
+    key = id(t[0])
+    del t
+    import gc
+    gc.collect()
+    assert key not in bp._PLANS
+
+
+def test_frame_shard_partition(pkg):
+    sh = pkg.sharding
+    for B in (1, 7, 8, 32, 64):
+        for G in (1, 2, 4, 8):
+            spans = [sh.frame_shard(B, r, G) for r in range(G)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sh.frame_shard(8, 2, 2)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    full = torch.arange(4 * 3 * 2 * 5 * 5, dtype=torch.float32).view(4, 3, 2, 5, 5)
+    (mine,) = pkg.sharding.shard_frames((full,), rank, world)
+    got, work = pkg.sharding.all_gather_bev(mine, async_op=(rank == 0))
+    if work is not None:
+        work.wait()
+    q.put((rank, bool(torch.equal(got, full)), tuple(mine.shape)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_frame_sharding_and_all_gather_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True, (2, 3, 2, 5, 5)), (1, True, (2, 3, 2, 5, 5))]

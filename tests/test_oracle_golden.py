@@ -136,7 +136,7 @@ def test_backward_is_gradient_of_forward(orc, golden):
         d = g["depth"].copy().reshape(-1)
         d[idx] += 0.5
         assert abs((loss(d.reshape(g["depth"].shape), feat_cl) - base) / 0.5 - gd.reshape(-1)[idx]) < 2e-3 * max(1, abs(gd.reshape(-1)[idx]))
-    for idx in (0, 777, 20001):
+    for idx in (0, 777, 4001):
         f = feat_cl.copy().reshape(-1)
         f[idx] += 0.5
         assert abs((loss(g["depth"], f.reshape(feat_cl.shape)) - base) / 0.5 - gf.reshape(-1)[idx]) < 2e-3 * max(1, abs(gf.reshape(-1)[idx]))
