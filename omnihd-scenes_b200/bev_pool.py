@@ -167,7 +167,7 @@ def _backward_general(out_grad_cl, depth, feat, rd, rf, rb):
     if n == 0:
         return depth_grad, feat_grad
     n_pixels = feat.numel() // feat.shape[-1]
-    bp = torch.empty((5, n), dtype=torch.int32, device=dev)     # rd, rf, rb, starts, lengths
+    bp = torch.empty((5, (n + 63) // 64 * 64), dtype=torch.int32, device=dev)[:, :n]   # rd, rf, rb, starts, lengths; rows 256 B aligned
     n_bp = torch.empty(1, dtype=torch.int32, device=dev)
     ws_bytes = lib.bevpool_v2_backward_regroup_workspace_bytes(n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)

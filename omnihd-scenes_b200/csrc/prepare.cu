@@ -309,7 +309,8 @@ segment_heads_kernel(const int* __restrict__ keys, const int* __restrict__ vals,
   if (tile_base >= n) return;
   const int64_t i0 = tile_base + (int64_t)tid * kHeadItems;
   int k[kHeadItems], v[kHeadItems];
-  if (i0 + kHeadItems <= n) {
+  const bool vec_ok = ((((uintptr_t)keys) | ((uintptr_t)vals)) & 15) == 0;   // caller buffers may be unaligned views
+  if (vec_ok && i0 + kHeadItems <= n) {
     const int4 kk = *reinterpret_cast<const int4*>(keys + i0);
     const int4 vv = *reinterpret_cast<const int4*>(vals + i0);
     k[0] = kk.x; k[1] = kk.y; k[2] = kk.z; k[3] = kk.w;
@@ -345,7 +346,7 @@ segment_heads_kernel(const int* __restrict__ keys, const int* __restrict__ vals,
     int f[kHeadItems];
 #pragma unroll
     for (int j = 0; j < kHeadItems; ++j) f[j] = (v[j] / dhw) * hw + v[j] % hw;
-    if (i0 + kHeadItems <= n) {
+    if ((((uintptr_t)ranks_feat) & 15) == 0 && i0 + kHeadItems <= n) {
       *reinterpret_cast<int4*>(ranks_feat + i0) = make_int4(f[0], f[1], f[2], f[3]);
     } else {
 #pragma unroll

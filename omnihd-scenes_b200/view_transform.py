@@ -105,9 +105,10 @@ def _prepare_device(coor, frustum, rots, trans, B, N, D, H, W, dx, bx, nx, devic
     if p0 >= 2 ** 30 or vtot >= 2 ** 31 - 1:
         raise ValueError("problem too large for int32 ranks: shard the frame batch")
     out = _Prepared()
-    ranks = torch.empty((3, max(p0, 1)), dtype=torch.int32, device=device)
+    pad = lambda n: (max(n, 1) + 63) // 64 * 64            # rows stay 256-byte aligned (128-bit loads)
+    ranks = torch.empty((3, pad(p0)), dtype=torch.int32, device=device)[:, :max(p0, 1)]
     n_int = max(min(p0, vtot), 1)
-    inter = torch.empty((2, n_int), dtype=torch.int32, device=device)
+    inter = torch.empty((2, pad(n_int)), dtype=torch.int32, device=device)[:, :n_int]
     out.rb, out.rd, out.rf = ranks[0], ranks[1], ranks[2]
     out.starts, out.lengths = inter[0], inter[1]
     out.counts = torch.empty(2, dtype=torch.int32, device=device)

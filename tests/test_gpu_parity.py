@@ -375,7 +375,7 @@ def test_bf16_io(pkg, orc):
     f = f16.clone().requires_grad_()
     bev = pkg.bev_pool_v2(d, f, cu(rd), cu(rf), cu(rb), shape, cu(st), cu(ln))
     assert bev.dtype == torch.bfloat16
-    assert rel_to_max(bev.float().permute(0, 2, 3, 4, 1).cpu().numpy(), ref) <= TOL_BF16
+    assert rel_to_max(bev.detach().float().permute(0, 2, 3, 4, 1).cpu().numpy(), ref) <= TOL_BF16
     bev.backward(g16)
     assert d.grad.dtype == torch.bfloat16 and f.grad.dtype == torch.bfloat16
     assert rel_to_max(d.grad.float().cpu().numpy(), gd) <= TOL_BF16
