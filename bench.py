@@ -280,33 +280,42 @@ def run_native_arm(args):
         bp = pkg.bev_pool
         prs = [pkg.view_transform._prepare_device(None, view.frustum, s["rots"], s["trans"], B, N, D, H, W,
                                                   view.dx, view.bx, view.nx, dev) for s in sets]
-        feat_cl = [s["feat"].detach().permute(0, 1, 3, 4, 2).contiguous() for s in sets]
+        feats = [s["feat"].detach() for s in sets]                                    # [B,N,C,H,W]
+        feat_cl = [f.new_empty((B * N, H, W, C)) for f in feats]
+        for f, fc in zip(feats, feat_cl):
+            bp._launch_transpose(f, fc, B * N, C, H * W, True)
         outs = [torch.empty((B, C, Z, Y, X), dtype=dt_t, device=dev) for _ in sets]
-        tables = [bp._launch_forward_dense(s["depth"].detach(), f, o, p.rd, p.rf, p.rb, p.starts, p.lengths, 0,
-                                           p.counts, V, X * Y * Z, pkg._lib.LAYOUT_BCZYX)
-                  for s, f, o, p in zip(sets, feat_cl, outs, prs)]
+        tables = [bp._launch_voxel_table(p.rb, p.p0, p.counts, V) for p in prs]
         og_cl = [torch.empty((B, Z, Y, X, C), dtype=dt_t, device=dev) for _ in sets]
         dgs = [torch.empty_like(s["depth"]) for s in sets]
-        fgs = [torch.empty_like(f) for f in feat_cl]
+        fgs = [torch.empty_like(f) for f in feats]
         code = bp._dtype_code(feat_cl[0])
         st = torch.cuda.current_stream().cuda_stream
 
         def k_fwd(i):
             k = i % N_BUFFER_SETS
             p = prs[k]
-            bp._launch_forward_dense(sets[k]["depth"].detach(), feat_cl[k], outs[k], p.rd, p.rf, p.rb, p.starts,
-                                     p.lengths, 0, p.counts, V, X * Y * Z, pkg._lib.LAYOUT_BCZYX, table=tables[k])
+            bp._launch_forward_dense(sets[k]["depth"].detach(), feat_cl[k], outs[k], p.rd, None, tables[k], B, Z * Y, X,
+                                     pkg._lib.LAYOUT_BCZYX, dhw=D * H * W, hw=H * W)
 
         def k_tr(i):
             k = i % N_BUFFER_SETS
             bp._launch_transpose(sets[k]["gout"], og_cl[k], B, C, X * Y * Z, True)
+
+        def k_trf(i):
+            k = i % N_BUFFER_SETS
+            bp._launch_transpose(feats[k], feat_cl[k], B * N, C, H * W, True)
+
+        def k_tbl(i):
+            k = i % N_BUFFER_SETS
+            lib.bevpool_voxel_table(prs[k].rb.data_ptr(), prs[k].p0, prs[k].counts.data_ptr(), V, tables[k].data_ptr(), st)
 
         def k_bwd(i):
             k = i % N_BUFFER_SETS
             p = prs[k]
             lib.bevpool_v2_backward_dense(og_cl[k].data_ptr(), dgs[k].data_ptr(), fgs[k].data_ptr(),
                                           sets[k]["depth"].data_ptr(), feat_cl[k].data_ptr(), p.point_rank.data_ptr(),
-                                          p.bn, p.d, p.hw, C, code, st)
+                                          p.bn, p.d, p.h, p.w, C, 1, code, st)
 
         def k_prep(i):
             k = i % N_BUFFER_SETS
@@ -315,7 +324,7 @@ def run_native_arm(args):
 
         reps = 40
         for name, fn in (("pool_fwd_dense", k_fwd), ("grid_transpose", k_tr), ("pool_bwd_dense", k_bwd),
-                         ("prepare_all", k_prep)):
+                         ("prepare_all", k_prep), ("feat_transpose", k_trf), ("voxel_table", k_tbl)):
             kernels[name] = timed_local(torch, fn, reps) * 1e-3      # seconds per launch
 
     if rank != 0:
@@ -344,6 +353,9 @@ def run_native_arm(args):
                                        "bytes": ab["bwd"]},
                     "grid_transpose(out_grad)": {"us": kernels["grid_transpose"] * 1e6,
                                                  "GBps": 2 * e * C * V / kernels["grid_transpose"] / 1e9},
+                    "feat_transpose": {"us": kernels["feat_transpose"] * 1e6,
+                                       "GBps": 2 * e * C * F / kernels["feat_transpose"] / 1e9},
+                    "voxel_table": {"us": kernels["voxel_table"] * 1e6},
                     "prepare(all kernels, eager launches)": {"us": kernels["prepare_all"] * 1e6, "bytes_out": ab["prep"]}},
                 "step_GBps_fwd_plus_bwd": (ab["fwd"] + ab["bwd"]) / (ms_step * 1e-3) / 1e9}
 

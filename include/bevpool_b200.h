@@ -17,9 +17,9 @@
  *   bevpool_v2_backward_regroup   ops/bev_pool_v2/bev_pool.py:47-57        argsort by ranks_feat + run-length
  *   bevpool_geometry              bevfusion/detectors/cam_stream_lss_bevpoolv2.py:244-251  get_geometry
  *   bevpool_prepare_v2            same file :294-351                        voxel_pooling_prepare_v2
- *   bevpool_v2_forward_dense /    the fused forms of the above used by the view-transform shim:
- *   bevpool_v2_backward_dense     bev_pool.py:27 (zeros) + :29 (kernel) + :91 (permute) in one pass;
- *                                 bev_pool.py:47-57,67-70 (argsort, zeros, kernel) in one pass
+ *   bevpool_voxel_table +         the fused forms of the above used by the view-transform shim:
+ *   bevpool_v2_forward_dense /    bev_pool.py:27 (zeros) + :29 (kernel) + :91 (permute) in one pass;
+ *   bevpool_v2_backward_dense     bev_pool.py:47-57,67-70 (argsort, zeros, kernel) in one pass
  *
  * Argument order note: like the reference's native entry points, interval_lengths
  * precedes interval_starts here (bev_pool.cpp:37-38), the opposite of the Python API.
@@ -123,28 +123,32 @@ int bevpool_prepare_v2(const float* coor, const float* frustum, const float* rot
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ fused ("dense") pooling
- * Forward that also zero-fills empty voxels and writes either layout directly.
- * n_intervals is read from counts_dev[1] on the device when counts_dev != NULL (no host sync),
- * else from the n_intervals argument. n_voxels_total = B*Z*Y*X, voxels_per_frame = Z*Y*X.
- * `out` need NOT be zeroed. workspace holds the strip->interval table: build_table != 0 rebuilds it
- * from the interval arrays first (one extra small launch); 0 re-uses the table a previous call with
- * the same interval arrays left there (fixed-camera inference, per-kernel timing). */
-size_t bevpool_v2_forward_dense_workspace_bytes(int64_t n_voxels_total, int64_t voxels_per_frame);
+ * Lower-bound table over the sorted voxel ranks: vox_pt[v] = number of sorted points with rank < v,
+ * for v in [0, n_voxels_total] (n_voxels_total + 1 entries); voxel v owns sorted points
+ * [vox_pt[v], vox_pt[v+1]). It stands in for interval_starts / interval_lengths on the device.
+ * n_points is the point count, or an upper bound with the true count read from counts_dev[0]. */
+int bevpool_voxel_table(const int32_t* ranks_bev_sorted, int64_t n_points, const int32_t* counts_dev,
+                        int64_t n_voxels_total, int32_t* vox_pt, void* stream);
+
+/* Forward that also zero-fills empty voxels and writes either layout directly (`out` need NOT be
+ * zeroed): new_zeros + kernel + permute of bev_pool.py:27,29,91 in one pass.
+ * ranks_depth is the sorted point list; ranks_bev must be non-decreasing (it is only used through
+ * vox_pt). ranks_feat may be NULL when it is derivable from ranks_depth, as for every output of
+ * voxel_pooling_prepare_v2: rf = (rd / dhw) * hw + rd % hw  (dhw = D*H*W, hw = H*W).
+ * The grid is n_frames x rows_per_frame (= Z*Y) x x voxels. */
 int bevpool_v2_forward_dense(const void* depth, const void* feat, void* out,
-                             const int32_t* ranks_depth, const int32_t* ranks_feat, const int32_t* ranks_bev,
-                             const int32_t* interval_lengths, const int32_t* interval_starts,
-                             int64_t n_intervals, const int32_t* counts_dev,
-                             int c, int64_t n_voxels_total, int64_t voxels_per_frame,
-                             int layout, int dtype, void* workspace, size_t workspace_bytes,
-                             int build_table, void* stream);
+                             const int32_t* ranks_depth, const int32_t* ranks_feat, const int32_t* vox_pt,
+                             int c, int64_t n_frames, int64_t rows_per_frame, int x, int dhw, int hw,
+                             int layout, int dtype, void* stream);
 
 /* Sort-free backward for rank arrays that came from bevpool_prepare_v2: walks the D depth
  * bins of every feature pixel through point_rank, writes EVERY element of depth_grad
- * ([B,N,D,H,W], zeros for dropped points) and feat_grad ([B,N,H,W,C]) — no memset, no argsort.
- * out_grad is [B,Z,Y,X,C] (use bevpool_grid_transpose for a [B,C,Z,Y,X] gradient). */
+ * ([BN,D,H,W], zeros for dropped points) and feat_grad — no memset, no argsort.
+ * out_grad is [B,Z,Y,X,C] (use bevpool_grid_transpose for a [B,C,Z,Y,X] gradient).
+ * feat is [BN,H,W,C]; feat_grad is [BN,H,W,C] (feat_grad_nchw == 0) or [BN,C,H,W] (!= 0). */
 int bevpool_v2_backward_dense(const void* out_grad, void* depth_grad, void* feat_grad,
                               const void* depth, const void* feat, const int32_t* point_rank,
-                              int bn, int d, int hw, int c, int dtype, void* stream);
+                              int bn, int d, int h, int w, int c, int feat_grad_nchw, int dtype, void* stream);
 
 /* [B,C,Z,Y,X] <-> [B,Z,Y,X,C] tile transpose (bev_pool.py:69 / :91 as one coalesced pass).
  * to_channels_last != 0: src is BCZYX, dst is BZYXC; else the reverse. */

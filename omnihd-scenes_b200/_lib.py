@@ -38,10 +38,10 @@ SIGNATURES = {
     "bevpool_prepare_v2_workspace_bytes": (c_size_t, [ctypes.POINTER(GridT)]),
     "bevpool_prepare_v2": (c_int, [c_void_p] * 4 + [ctypes.POINTER(GridT)] + [c_void_p] * 7 +
                            [c_void_p, c_size_t, c_void_p]),
-    "bevpool_v2_forward_dense_workspace_bytes": (c_size_t, [c_i64, c_i64]),
-    "bevpool_v2_forward_dense": (c_int, [c_void_p] * 8 + [c_i64, c_void_p, c_int, c_i64, c_i64, c_int, c_int,
-                                                          c_void_p, c_size_t, c_int, c_void_p]),
-    "bevpool_v2_backward_dense": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "bevpool_voxel_table": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p]),
+    "bevpool_v2_forward_dense": (c_int, [c_void_p] * 6 + [c_int, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int,
+                                                          c_void_p]),
+    "bevpool_v2_backward_dense": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_void_p]),
     "bevpool_grid_transpose": (c_int, [c_void_p, c_void_p, c_int, c_int, c_i64, c_int, c_int, c_void_p]),
 }
 

@@ -97,10 +97,10 @@ class PreparePlan:
     that lets the backward walk a pixel's depth bins without sorting by ranks_feat.
     """
 
-    def __init__(self, tensors, point_rank, bn, d, hw):
+    def __init__(self, tensors, point_rank, bn, d, h, w):
         self.refs = [weakref.ref(t) for t in tensors]
         self.versions = [t._version for t in tensors]
-        self.point_rank, self.bn, self.d, self.hw = point_rank, bn, d, hw
+        self.point_rank, self.bn, self.d, self.h, self.w, self.hw = point_rank, bn, d, h, w, h * w
 
     def matches(self, tensors):
         return all(r() is t and t._version == v for r, t, v in zip(self.refs, tensors, self.versions))
@@ -109,10 +109,10 @@ class PreparePlan:
 _PLANS = {}
 
 
-def register_plan(ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths, point_rank, bn, d, hw):
+def register_plan(ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths, point_rank, bn, d, h, w):
     tensors = (ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths)
     key = id(ranks_bev)
-    _PLANS[key] = PreparePlan(tensors, point_rank, bn, d, hw)
+    _PLANS[key] = PreparePlan(tensors, point_rank, bn, d, h, w)
     weakref.finalize(ranks_bev, _PLANS.pop, key, None)
 
 
@@ -133,22 +133,21 @@ def _launch_forward(depth, feat, out, rd, rf, rb, starts, lengths):
                                       _dtype_code(feat), _stream()), "bevpool_v2_forward")
 
 
-def _launch_forward_dense(depth, feat, out, rd, rf, rb, starts, lengths, n_intervals, counts_dev, n_vox_total,
-                          vox_per_frame, layout, table=None):
-    """table: an int32 tensor that already holds the strip table (skips the table kernel)."""
+def _launch_voxel_table(rb_sorted, n_points, counts_dev, n_vox_total):
+    """vox_pt[v] = #sorted points with rank < v; stands in for the interval arrays on the device."""
     lib = _lib.load()
-    ws_bytes = lib.bevpool_v2_forward_dense_workspace_bytes(n_vox_total, vox_per_frame)
-    build = 1
-    if table is not None:
-        ws, build = table, 0
-    else:
-        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=feat.device)
-    _lib.check(lib.bevpool_v2_forward_dense(_ptr(depth), _ptr(feat), _ptr(out), _ptr(rd), _ptr(rf), _ptr(rb),
-                                            _ptr(lengths), _ptr(starts), n_intervals, _ptr(counts_dev),
-                                            feat.shape[-1], n_vox_total, vox_per_frame, layout, _dtype_code(feat),
-                                            _ptr(ws), ws.numel() * ws.element_size(), build, _stream()),
-               "bevpool_v2_forward_dense")
-    return ws
+    vox_pt = torch.empty(n_vox_total + 1, dtype=torch.int32, device=rb_sorted.device)
+    _lib.check(lib.bevpool_voxel_table(_ptr(rb_sorted), n_points, _ptr(counts_dev), n_vox_total, _ptr(vox_pt),
+                                       _stream()), "bevpool_voxel_table")
+    return vox_pt
+
+
+def _launch_forward_dense(depth, feat, out, rd, rf, vox_pt, frames, rows, x, layout, dhw=0, hw=0):
+    """rf=None: ranks_feat is derived from ranks_depth on the fly (dhw = D*H*W, hw = H*W)."""
+    lib = _lib.load()
+    _lib.check(lib.bevpool_v2_forward_dense(_ptr(depth), _ptr(feat), _ptr(out), _ptr(rd), _ptr(rf), _ptr(vox_pt),
+                                            feat.shape[-1], frames, rows, x, dhw, hw, layout, _dtype_code(feat),
+                                            _stream()), "bevpool_v2_forward_dense")
 
 
 def _launch_transpose(src, dst, b, c, zyx, to_channels_last):
@@ -188,8 +187,8 @@ def _backward_dense(out_grad_cl, depth, feat, plan):
     depth_grad = torch.empty_like(depth)
     feat_grad = torch.empty_like(feat)
     _lib.check(lib.bevpool_v2_backward_dense(_ptr(out_grad_cl), _ptr(depth_grad), _ptr(feat_grad), _ptr(depth),
-                                             _ptr(feat), _ptr(plan.point_rank), plan.bn, plan.d, plan.hw,
-                                             feat.shape[-1], _dtype_code(feat), _stream()),
+                                             _ptr(feat), _ptr(plan.point_rank), plan.bn, plan.d, plan.h, plan.w,
+                                             feat.shape[-1], 0, _dtype_code(feat), _stream()),
                "bevpool_v2_backward_dense")
     return depth_grad, feat_grad
 
@@ -231,16 +230,21 @@ class _BevPoolV2Fused(torch.autograd.Function):
         ctx.plan = _find_plan(*plan_key, depth, feat)
         ctx.shape = (B, Z, Y, X, C)
         ctx.in_dtypes = (in_depth_dtype, in_feat_dtype)
-        if C % 4 != 0:
-            # odd channel counts (the reference's KAT has C=2): scalar kernel + transpose kernel
+        # the fused kernel walks voxels in rank order: it needs non-decreasing ranks_bev. Tensors that
+        # came from our prepare are sorted by construction; anything else is checked (one small sync).
+        fused_ok = C % 4 == 0 and rb.numel() > 0 and feat.data_ptr() % 16 == 0 and \
+            (ctx.plan is not None or bool((rb[1:] >= rb[:-1]).all()))
+        if not fused_ok:
+            # odd channel counts (the reference's KAT has C=2) or unsorted intervals:
+            # reference-contract kernel + transpose kernel
             out_cl = feat.new_zeros((B, Z, Y, X, C))
             _launch_forward(depth, feat, out_cl, rd, rf, rb, starts, lengths)
             out = feat.new_empty((B, C, Z, Y, X))
             _launch_transpose(out_cl, out, B, C, Z * Y * X, to_channels_last=False)
         else:
             out = feat.new_empty((B, C, Z, Y, X))
-            _launch_forward_dense(depth, feat, out, rd, rf, rb, starts, lengths, starts.numel(), None,
-                                  B * Z * Y * X, Z * Y * X, _lib.LAYOUT_BCZYX)
+            vox_pt = _launch_voxel_table(rb, rb.numel(), None, B * Z * Y * X)
+            _launch_forward_dense(depth, feat, out, rd, rf, vox_pt, B, Z * Y, X, _lib.LAYOUT_BCZYX)
         ctx.save_for_backward(rb, depth, feat, rf, rd)
         return out
 
@@ -287,12 +291,11 @@ class TRTBEVPoolv2(torch.autograd.Function):
         depth, feat, rd, rf, rb, starts, lengths = _canon_inputs(depth, feat, ranks_depth, ranks_feat, ranks_bev,
                                                                  interval_starts, interval_lengths)
         C = feat.shape[-1]
-        if C % 4 != 0:
+        if C % 4 != 0 or rb.numel() == 0 or not bool((rb[1:] >= rb[:-1]).all()):
             out = feat.new_zeros((1, out_height, out_width, C))
             _launch_forward(depth, feat, out, rd, rf, rb, starts, lengths)
             return out
         out = feat.new_empty((1, out_height, out_width, C))
-        n_vox = out_height * out_width
-        _launch_forward_dense(depth, feat, out, rd, rf, rb, starts, lengths, starts.numel(), None, n_vox, n_vox,
-                              _lib.LAYOUT_BZYXC)
+        vox_pt = _launch_voxel_table(rb, rb.numel(), None, out_height * out_width)
+        _launch_forward_dense(depth, feat, out, rd, rf, vox_pt, 1, out_height, out_width, _lib.LAYOUT_BZYXC)
         return out

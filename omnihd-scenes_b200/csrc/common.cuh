@@ -72,6 +72,7 @@ struct Vec4<float> {
   }
   static __device__ __forceinline__ float load1(const float* base, int64_t elem) { return __ldg(base + elem); }
   static __device__ __forceinline__ void store1(float* base, int64_t elem, float v) { base[elem] = v; }
+  static __device__ __forceinline__ void store1s(float* base, int64_t elem, float v) { stg_stream_f32(base + elem, v); }
 };
 template <>
 struct Vec4<__nv_bfloat16> {
@@ -103,6 +104,9 @@ struct Vec4<__nv_bfloat16> {
     return __bfloat162float(base[elem]);
   }
   static __device__ __forceinline__ void store1(__nv_bfloat16* base, int64_t elem, float v) {
+    base[elem] = __float2bfloat16_rn(v);
+  }
+  static __device__ __forceinline__ void store1s(__nv_bfloat16* base, int64_t elem, float v) {
     base[elem] = __float2bfloat16_rn(v);
   }
 };

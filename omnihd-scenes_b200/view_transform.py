@@ -19,7 +19,7 @@ from torch import nn
 
 from . import _lib
 from .bev_pool import bev_pool_v2, register_plan, _ptr, _stream, _launch_forward_dense, _launch_transpose, \
-    _dtype_code
+    _launch_voxel_table, _dtype_code
 
 
 # ----------------------------------------------------------------------------- constants
@@ -94,7 +94,7 @@ def get_geometry(frustum, rots, trans):
 # ----------------------------------------------------------------------------- prepare
 class _Prepared:
     """Worst-case-sized device outputs of one prepare call (no host sync yet)."""
-    __slots__ = ("rb", "rd", "rf", "starts", "lengths", "counts", "point_rank", "bn", "d", "hw", "p0")
+    __slots__ = ("rb", "rd", "rf", "starts", "lengths", "counts", "point_rank", "bn", "d", "h", "w", "hw", "p0")
 
 
 def _prepare_device(coor, frustum, rots, trans, B, N, D, H, W, dx, bx, nx, device):
@@ -113,7 +113,7 @@ def _prepare_device(coor, frustum, rots, trans, B, N, D, H, W, dx, bx, nx, devic
     out.starts, out.lengths = inter[0], inter[1]
     out.counts = torch.empty(2, dtype=torch.int32, device=device)
     out.point_rank = torch.empty(max(p0, 1), dtype=torch.int32, device=device)
-    out.bn, out.d, out.hw, out.p0 = B * N, D, H * W, p0
+    out.bn, out.d, out.h, out.w, out.hw, out.p0 = B * N, D, H, W, H * W, p0
     ws_bytes = lib.bevpool_prepare_v2_workspace_bytes(g)
     ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=device)
     import ctypes
@@ -145,26 +145,32 @@ def voxel_pooling_prepare_v2(coor, dx, bx, nx):
     if P == 0 or I == 0:
         return None, None, None, None, None
     res = (pr.rb[:P], pr.rd[:P], pr.rf[:P], pr.starts[:I], pr.lengths[:I])
-    register_plan(*res, pr.point_rank, pr.bn, pr.d, pr.hw)
+    register_plan(*res, pr.point_rank, pr.bn, pr.d, pr.h, pr.w)
     return res
 
 
 # ----------------------------------------------------------------------------- fused module path
 class _FusedViewPool(torch.autograd.Function):
-    """geometry -> rank -> sort -> pool with no host synchronisation: interval / point counts stay
-    on the device (counts_dev), buffers are worst-case sized. Backward is the sort-free kernel."""
+    """geometry -> rank -> sort -> pool with no host synchronisation: point counts stay on the device
+    (counts_dev), buffers are worst-case sized. Takes feat as the neck produces it ([B,N,C,H,W]); the
+    NCHW->NHWC transpose (reference :282), the zero fill, the pooling and the output permute are our
+    kernels, and the backward is the sort-free kernel writing feat_grad straight back in [B,N,C,H,W]."""
 
     @staticmethod
-    def forward(ctx, depth, feat_cl, prepared, shape):
+    def forward(ctx, depth, feat, prepared, shape):
         B, Z, Y, X, C = shape
+        pr = prepared
         depth = depth.contiguous()
-        feat_cl = feat_cl.contiguous()
-        if depth.dtype != feat_cl.dtype:
-            depth, feat_cl = depth.float(), feat_cl.float()
-        out = feat_cl.new_empty((B, C, Z, Y, X))
-        _launch_forward_dense(depth, feat_cl, out, prepared.rd, prepared.rf, prepared.rb, prepared.starts,
-                              prepared.lengths, 0, prepared.counts, B * Z * Y * X, Z * Y * X, _lib.LAYOUT_BCZYX)
-        ctx.prepared, ctx.shape = prepared, shape
+        feat = feat.contiguous()
+        if depth.dtype != feat.dtype or depth.dtype not in (torch.float32, torch.bfloat16):
+            depth, feat = depth.float(), feat.float()
+        feat_cl = feat.new_empty((pr.bn, pr.h, pr.w, C))
+        _launch_transpose(feat, feat_cl, pr.bn, C, pr.hw, True)           # [BN,C,HW] -> [BN,HW,C]
+        vox_pt = _launch_voxel_table(pr.rb, pr.p0, pr.counts, B * Z * Y * X)
+        out = feat.new_empty((B, C, Z, Y, X))
+        _launch_forward_dense(depth, feat_cl, out, pr.rd, None, vox_pt, B, Z * Y, X, _lib.LAYOUT_BCZYX,
+                              dhw=pr.d * pr.hw, hw=pr.hw)
+        ctx.prepared, ctx.shape, ctx.feat_shape = pr, shape, feat.shape
         ctx.save_for_backward(depth, feat_cl)
         return out
 
@@ -177,10 +183,10 @@ class _FusedViewPool(torch.autograd.Function):
         og_cl = out_grad.new_empty((B, Z, Y, X, C))
         _launch_transpose(out_grad, og_cl, B, C, Z * Y * X, True)
         depth_grad = torch.empty_like(depth)
-        feat_grad = torch.empty_like(feat_cl)
+        feat_grad = feat_cl.new_empty(ctx.feat_shape)                     # [B,N,C,H,W]
         lib = _lib.load()
         _lib.check(lib.bevpool_v2_backward_dense(_ptr(og_cl), _ptr(depth_grad), _ptr(feat_grad), _ptr(depth),
-                                                 _ptr(feat_cl), _ptr(pr.point_rank), pr.bn, pr.d, pr.hw, C,
+                                                 _ptr(feat_cl), _ptr(pr.point_rank), pr.bn, pr.d, pr.h, pr.w, C, 1,
                                                  _dtype_code(feat_cl), _stream()), "bevpool_v2_backward_dense")
         return depth_grad, feat_grad, None, None
 
@@ -256,6 +262,5 @@ class LSSViewTransform(nn.Module):
             raise ValueError("the fused path needs C % 4 == 0; use voxel_pooling_v2 for other channel counts")
         pr = _prepare_device(None, self.frustum, rots.contiguous(), trans.contiguous(), B, N, D, H, W,
                              self.dx, self.bx, self.nx, rots.device)
-        feat_cl = feat.permute(0, 1, 3, 4, 2).contiguous()
         shape = (B, int(self.nx[2]), int(self.nx[1]), int(self.nx[0]), C)
-        return _FusedViewPool.apply(depth, feat_cl, pr, shape)
+        return _FusedViewPool.apply(depth, feat, pr, shape)

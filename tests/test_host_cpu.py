@@ -98,7 +98,7 @@ def test_plugin_install_registers_reference_module_path(pkg):
 def test_plan_registry_is_identity_and_version_checked(pkg):
     bp = pkg.bev_pool
     t = [torch.zeros(4, dtype=torch.int32) for _ in range(5)]
-    bp.register_plan(*t, point_rank=torch.zeros(8, dtype=torch.int32), bn=1, d=2, hw=4)
+    bp.register_plan(*t, point_rank=torch.zeros(8, dtype=torch.int32), bn=1, d=2, h=2, w=2)
     depth, feat = torch.zeros(8), torch.zeros(4, 3)
     assert bp._find_plan(*t, depth, feat) is not None
     assert bp._find_plan(t[0], t[1].clone(), t[2], t[3], t[4], depth, feat) is None      # different object
