@@ -295,7 +295,7 @@ def run_native_arm(args):
         def k_fwd(i):
             k = i % N_BUFFER_SETS
             p = prs[k]
-            bp._launch_forward_dense(sets[k]["depth"].detach(), feat_cl[k], outs[k], p.rd, None, tables[k], B, Z * Y, X,
+            bp._launch_forward_dense(sets[k]["depth"].detach(), feat_cl[k], outs[k], p.rd, None, p.rb, tables[k], B, Z * Y, X,
                                      pkg._lib.LAYOUT_BCZYX, dhw=D * H * W, hw=H * W)
 
         def k_tr(i):

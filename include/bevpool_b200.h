@@ -132,13 +132,12 @@ int bevpool_voxel_table(const int32_t* ranks_bev_sorted, int64_t n_points, const
 
 /* Forward that also zero-fills empty voxels and writes either layout directly (`out` need NOT be
  * zeroed): new_zeros + kernel + permute of bev_pool.py:27,29,91 in one pass.
- * ranks_depth is the sorted point list; ranks_bev must be non-decreasing (it is only used through
- * vox_pt). ranks_feat may be NULL when it is derivable from ranks_depth, as for every output of
+ * ranks_depth / ranks_bev are the sorted per-point lists; ranks_bev must be non-decreasing. ranks_feat may be NULL when it is derivable from ranks_depth, as for every output of
  * voxel_pooling_prepare_v2: rf = (rd / dhw) * hw + rd % hw  (dhw = D*H*W, hw = H*W).
  * The grid is n_frames x rows_per_frame (= Z*Y) x x voxels. */
 int bevpool_v2_forward_dense(const void* depth, const void* feat, void* out,
-                             const int32_t* ranks_depth, const int32_t* ranks_feat, const int32_t* vox_pt,
-                             int c, int64_t n_frames, int64_t rows_per_frame, int x, int dhw, int hw,
+                             const int32_t* ranks_depth, const int32_t* ranks_feat, const int32_t* ranks_bev,
+                             const int32_t* vox_pt, int c, int64_t n_frames, int64_t rows_per_frame, int x, int dhw, int hw,
                              int layout, int dtype, void* stream);
 
 /* Sort-free backward for rank arrays that came from bevpool_prepare_v2: walks the D depth

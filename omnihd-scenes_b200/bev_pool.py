@@ -142,10 +142,10 @@ def _launch_voxel_table(rb_sorted, n_points, counts_dev, n_vox_total):
     return vox_pt
 
 
-def _launch_forward_dense(depth, feat, out, rd, rf, vox_pt, frames, rows, x, layout, dhw=0, hw=0):
+def _launch_forward_dense(depth, feat, out, rd, rf, rb, vox_pt, frames, rows, x, layout, dhw=0, hw=0):
     """rf=None: ranks_feat is derived from ranks_depth on the fly (dhw = D*H*W, hw = H*W)."""
     lib = _lib.load()
-    _lib.check(lib.bevpool_v2_forward_dense(_ptr(depth), _ptr(feat), _ptr(out), _ptr(rd), _ptr(rf), _ptr(vox_pt),
+    _lib.check(lib.bevpool_v2_forward_dense(_ptr(depth), _ptr(feat), _ptr(out), _ptr(rd), _ptr(rf), _ptr(rb), _ptr(vox_pt),
                                             feat.shape[-1], frames, rows, x, dhw, hw, layout, _dtype_code(feat),
                                             _stream()), "bevpool_v2_forward_dense")
 
@@ -244,7 +244,7 @@ class _BevPoolV2Fused(torch.autograd.Function):
         else:
             out = feat.new_empty((B, C, Z, Y, X))
             vox_pt = _launch_voxel_table(rb, rb.numel(), None, B * Z * Y * X)
-            _launch_forward_dense(depth, feat, out, rd, rf, vox_pt, B, Z * Y, X, _lib.LAYOUT_BCZYX)
+            _launch_forward_dense(depth, feat, out, rd, rf, rb, vox_pt, B, Z * Y, X, _lib.LAYOUT_BCZYX)
         ctx.save_for_backward(rb, depth, feat, rf, rd)
         return out
 
@@ -297,5 +297,5 @@ class TRTBEVPoolv2(torch.autograd.Function):
             return out
         out = feat.new_empty((1, out_height, out_width, C))
         vox_pt = _launch_voxel_table(rb, rb.numel(), None, out_height * out_width)
-        _launch_forward_dense(depth, feat, out, rd, rf, vox_pt, 1, out_height, out_width, _lib.LAYOUT_BZYXC)
+        _launch_forward_dense(depth, feat, out, rd, rf, rb, vox_pt, 1, out_height, out_width, _lib.LAYOUT_BZYXC)
         return out

@@ -111,12 +111,13 @@ struct Vec4<__nv_bfloat16> {
   }
 };
 
+// Blackwell packed FP32: one FFMA2 issues two IEEE fused multiply-adds (same rounding as fmaf), which
+// halves the FMA instruction count of these issue-bound kernels.
 __device__ __forceinline__ float4 fma4(float4 a, float s, float4 acc) {
-  acc.x = fmaf(a.x, s, acc.x);
-  acc.y = fmaf(a.y, s, acc.y);
-  acc.z = fmaf(a.z, s, acc.z);
-  acc.w = fmaf(a.w, s, acc.w);
-  return acc;
+  const float2 s2 = make_float2(s, s);
+  const float2 lo = __ffma2_rn(make_float2(a.x, a.y), s2, make_float2(acc.x, acc.y));
+  const float2 hi = __ffma2_rn(make_float2(a.z, a.w), s2, make_float2(acc.z, acc.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 __device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
   acc = fmaf(a.x, b.x, acc);
@@ -124,6 +125,12 @@ __device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
   acc = fmaf(a.z, b.z, acc);
   acc = fmaf(a.w, b.w, acc);
   return acc;
+}
+// <a, b> with two packed FMAs and one add (summation order differs from dot4: tolerance-level only)
+__device__ __forceinline__ float dot4_packed(float4 a, float4 b) {
+  float2 p = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(0.f, 0.f));
+  p = __ffma2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), p);
+  return p.x + p.y;
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

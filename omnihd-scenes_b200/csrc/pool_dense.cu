@@ -21,6 +21,8 @@
 //                          Replaces argsort + where + 2x new_zeros + kernel (bev_pool.py:47-70).
 //
 // No atomics anywhere; every sum has a fixed order, so results are run-to-run deterministic.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace bevpool {
@@ -64,112 +66,152 @@ constexpr int kTileX = 32;
 constexpr int kTileRows = 4;
 constexpr int kTileCols = kTileX * kTileRows;  // 128 voxel columns
 constexpr int kTileStride = kTileCols + 1;     // +1: conflict-free row reads at write-out
-constexpr int kFwdWarps = 8;
-constexpr int kFwdThreads = kFwdWarps * 32;
-constexpr int kGroup = 8;          // voxels per work item
-constexpr int kLongVoxel = 512;    // voxels with more points are summed by the whole CTA
+constexpr int kFwdMaxWarps = 16;
+constexpr int kMaxItems = 2 * kFwdMaxWarps + kTileRows;   // chunks per tile (upper bound)
 
 struct FwdParams {
   int c;                 // channels
   int x;                 // X
   int64_t rows;          // Z*Y rows per frame
   int64_t frames;
-  int dhw, hw;           // to derive ranks_feat from ranks_depth when rf == nullptr
+  int chunks_per_warp;   // target work items per warp and tile
+  int hw;                // H*W            } to derive ranks_feat from ranks_depth when rf == nullptr:
+  uint32_t dhw_mul;      // magic multiplier } rd / (D*H*W) == (rd * dhw_mul) >> dhw_shift   (rd < 2^31)
+  int dhw_shift, dhw;
 };
 
-// Per-point scalars of one batch: one lane per point.
+// Per-point scalars of one batch, one lane per point: feature-row index, depth weight and the tile
+// column of the point's voxel.
 template <typename T>
-__device__ __forceinline__ void load_point(const T* __restrict__ depth, const int* __restrict__ rf, int rd_val,
-                                           int64_t p, const FwdParams& prm, int c4, int& off4, float& d) {
-  // feature-row offset in float4 units; derived from ranks_depth when the caller has no ranks_feat
-  const int f = rf ? ldg_stream_i32(rf + p) : (rd_val / prm.dhw) * prm.hw + rd_val % prm.hw;
-  off4 = f * c4;
+__device__ __forceinline__ void load_point(const T* __restrict__ depth, const int* __restrict__ rf,
+                                           const int* __restrict__ rb, int rd_val, int p, const FwdParams& prm,
+                                           int rank_col0, int& f, float& d, int& col) {
+  if (rf) {
+    f = ldg_stream_i32(rf + p);
+  } else {
+    const int cam = (int)(((uint64_t)(uint32_t)rd_val * prm.dhw_mul) >> prm.dhw_shift);   // rd / DHW
+    const int rem = rd_val - cam * prm.dhw;                                                // d*HW + hw
+    f = cam * prm.hw + rem % prm.hw;
+  }
   d = Vec4<T>::load1(depth, rd_val);
+  col = ldg_stream_i32(rb + p) - rank_col0;
 }
 
-// Sum points [p, pe) of tile row `row_pt` (shared-memory copy of vox_pt for that row, relative voxel
-// index) starting in voxel `cur`; flush the running sum into column col0+cur of the tile each time the
-// voxel changes. BOUNDS=false: single voxel slice, nothing is flushed, the sum is returned.
-template <typename T, bool BOUNDS>
-__device__ __forceinline__ float4 flat_sum(const T* __restrict__ depth, const T* __restrict__ feat,
-                                           const int* __restrict__ rd, const int* __restrict__ rf, int64_t p,
-                                           int64_t pe, const FwdParams& prm, int c4, int cb, bool act,
-                                           const int* row_pt, int cur, float* tile_col0) {
+__device__ __forceinline__ void flush_column(float* tile_lane, int col, float4 acc) {
+  float* c = tile_lane + col;
+  c[0 * kTileStride] = acc.x;
+  c[1 * kTileStride] = acc.y;
+  c[2 * kTileStride] = acc.z;
+  c[3 * kTileStride] = acc.w;
+}
+
+// One work item: sorted points [p, pe) of one tile row, walked FLAT with 8 feature rows in flight.
+// A running sum is flushed each time the voxel changes: complete voxels go straight into their tile
+// column; the first / last voxel of the chunk, when cut by the chunk boundary, go to the item's two
+// partial slots (part_lane = &part[item][0][4*lane], second slot at +cw) and are added to the tile in
+// item order afterwards, so the summation order is fixed.
+// feat_lane = feat + this lane's channel chunk; idle lanes alias the last chunk (never stored).
+template <typename T>
+__device__ __forceinline__ void chunk_sum(const T* __restrict__ depth, const T* __restrict__ feat_lane,
+                                          const int* __restrict__ rd, const int* __restrict__ rf,
+                                          const int* __restrict__ rb, int p, int pe, bool head_partial,
+                                          bool tail_partial, const FwdParams& prm, int rank_col0, float* tile_lane,
+                                          float* part_lane, int* part_col, int cw, bool act) {
   const int lane = lane_id();
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 acc = zero;
-  if (p >= pe) return acc;
-  const float4* __restrict__ feat4 = reinterpret_cast<const float4*>(feat);
-  int64_t next_b = BOUNDS ? (int64_t)row_pt[cur + 1] : pe;
 
-  // software pipeline: ranks_depth two batches ahead, (offset, depth) one batch ahead
-  int rd1 = (p + lane < pe) ? ldg_stream_i32(rd + p + lane) : 0;
+  // software pipeline: ranks_depth two batches ahead, (row, depth, column) one batch ahead
   int rd2 = (p + 32 + lane < pe) ? ldg_stream_i32(rd + p + 32 + lane) : 0;
-  int off_n = 0;
+  int f_n = 0, col_n = 0;
   float d_n = 0.f;
-  if (p + lane < pe) load_point<T>(depth, rf, rd1, p + lane, prm, c4, off_n, d_n);
+  if (p + lane < pe)
+    load_point<T>(depth, rf, rb, ldg_stream_i32(rd + p + lane), p + lane, prm, rank_col0, f_n, d_n, col_n);
+  int cur_col = __shfl_sync(kFullMask, col_n, 0);   // column of the first point
+  int carry = cur_col;
+  bool first_seg = true;
 
-  for (int64_t q = p; q < pe; q += 32) {
-    const int my_off = off_n;
+  auto flush = [&](bool last) {
+    const bool to_part = (first_seg && head_partial) || (last && tail_partial);
+    if (to_part) {
+      const int slot = first_seg ? 0 : 1;   // a chunk inside one voxel uses the head slot only
+      if (act) *reinterpret_cast<float4*>(part_lane + slot * cw) = acc;
+      if (lane == 0) part_col[slot] = cur_col;
+    } else if (act) {
+      flush_column(tile_lane, cur_col, acc);
+    }
+    first_seg = false;
+  };
+
+  for (int q = p; q < pe; q += 32) {
+    const int my_f = f_n, my_col = col_n;
     const float my_d = d_n;
-    // issue the prefetches for the following batches before touching this one
     const int rd_next = rd2;
     rd2 = (q + 64 + lane < pe) ? ldg_stream_i32(rd + q + 64 + lane) : 0;
-    off_n = 0;
-    d_n = 0.f;
-    if (q + 32 + lane < pe) load_point<T>(depth, rf, rd_next, q + 32 + lane, prm, c4, off_n, d_n);
+    f_n = 0; col_n = 0; d_n = 0.f;
+    if (q + 32 + lane < pe)
+      load_point<T>(depth, rf, rb, rd_next, q + 32 + lane, prm, rank_col0, f_n, d_n, col_n);
 
-    const int n = (int)min((int64_t)32, pe - q);
-    for (int i0 = 0; i0 < n; i0 += 8) {
-      float4 v[8];
+    const int n = min(32, pe - q);
+    int prev = __shfl_up_sync(kFullMask, my_col, 1);
+    if (lane == 0) prev = carry;
+    const unsigned bmask = __ballot_sync(kFullMask, lane < n && my_col != prev);   // bit i: point i opens a voxel
+    carry = __shfl_sync(kFullMask, my_col, n - 1);
+    if (n == 32) {
+#pragma unroll 1
+      for (int i0 = 0; i0 < 32; i0 += 8) {
+        float4 v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int off = __shfl_sync(kFullMask, my_off, i0 + u);
-        v[u] = (act && i0 + u < n) ? (sizeof(T) == 4 ? __ldg(feat4 + off + cb + lane)
-                                                     : Vec4<T>::load(feat, ((int64_t)off + cb + lane) * 4))
-                                   : zero;
-      }
+        for (int u = 0; u < 8; ++u)
+          v[u] = Vec4<T>::load(feat_lane, (int64_t)__shfl_sync(kFullMask, my_f, i0 + u) * prm.c);
+        const unsigned m8 = bmask >> i0;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float dd = __shfl_sync(kFullMask, my_d, i0 + u);
-        if (BOUNDS) {
-          // warp-uniform: leave the current voxel (and skip empty ones) before consuming point q+i0+u
-          while (i0 + u < n && q + i0 + u == next_b) {
-            if (act) {
-              float* col = tile_col0 + cur;
-              col[(4 * lane + 0) * kTileStride] = acc.x;
-              col[(4 * lane + 1) * kTileStride] = acc.y;
-              col[(4 * lane + 2) * kTileStride] = acc.z;
-              col[(4 * lane + 3) * kTileStride] = acc.w;
-            }
+        for (int u = 0; u < 8; ++u) {
+          const float dd = __shfl_sync(kFullMask, my_d, i0 + u);
+          if (m8 & (1u << u)) {   // warp-uniform
+            flush(false);
+            cur_col = __shfl_sync(kFullMask, my_col, i0 + u);
             acc = zero;
-            do { ++cur; next_b = row_pt[cur + 1]; } while (next_b == q + i0 + u);
           }
+          acc = fma4(v[u], dd, acc);
         }
-        acc = fma4(v[u], dd, acc);  // masked points carry v == 0
+      }
+    } else {
+      for (int i0 = 0; i0 < n; i0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int f = __shfl_sync(kFullMask, my_f, i0 + u);
+          v[u] = (i0 + u < n) ? Vec4<T>::load(feat_lane, (int64_t)f * prm.c) : zero;
+        }
+        const unsigned m8 = bmask >> i0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float dd = __shfl_sync(kFullMask, my_d, i0 + u);
+          if (m8 & (1u << u)) {
+            flush(false);
+            cur_col = __shfl_sync(kFullMask, my_col, i0 + u);
+            acc = zero;
+          }
+          acc = fma4(v[u], dd, acc);   // masked points carry v == 0 and d == 0
+        }
       }
     }
   }
-  if (BOUNDS && act) {
-    float* col = tile_col0 + cur;
-    col[(4 * lane + 0) * kTileStride] = acc.x;
-    col[(4 * lane + 1) * kTileStride] = acc.y;
-    col[(4 * lane + 2) * kTileStride] = acc.z;
-    col[(4 * lane + 3) * kTileStride] = acc.w;
-  }
-  return acc;
+  flush(true);
 }
 
-template <typename T, int LAYOUT>
-__global__ void __launch_bounds__(kFwdThreads)
+template <typename T, int LAYOUT, int MINB>
+__global__ void __launch_bounds__(kFwdMaxWarps * 32, MINB)
 pool_fwd_tile_kernel(const T* __restrict__ depth, const T* __restrict__ feat, T* __restrict__ out,
-                     const int* __restrict__ rd, const int* __restrict__ rf, const int* __restrict__ vox_pt,
-                     FwdParams prm, int tiles_x, int64_t tiles_per_frame) {
-  extern __shared__ float tile[];                       // [cw][kTileStride]
-  __shared__ int s_pt[kTileRows][kTileX + 1];           // vox_pt of the tile rows (+ closing entry)
-  __shared__ float4 s_partial[kFwdWarps][32];
-  __shared__ int s_next;
+                     const int* __restrict__ rd, const int* __restrict__ rf, const int* __restrict__ rb,
+                     const int* __restrict__ vox_pt, FwdParams prm, int tiles_x, int64_t tiles_per_frame) {
+  extern __shared__ float smem[];                 // tile [cw][kTileStride], then partial sums [kMaxItems][2][cw]
+  __shared__ int s_col[kMaxItems][2];             // tile column of each partial (-1: none)
+  __shared__ int s_row_lo[kTileRows + 1], s_row_hi[kTileRows], s_item0[kTileRows + 1];
+  __shared__ int s_next, s_chunk;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int n_threads = blockDim.x, n_warps = blockDim.x >> 5;
   const int c4 = prm.c >> 2;
 
   const int64_t t = blockIdx.x;
@@ -183,92 +225,102 @@ pool_fwd_tile_kernel(const T* __restrict__ depth, const T* __restrict__ feat, T*
   const int64_t vpf = prm.rows * prm.x;
   const int64_t rank0 = frame * vpf + row0 * prm.x + x0;                  // rank of (row0, x0)
 
-  for (int i = threadIdx.x; i < kTileRows * (kTileX + 1); i += kFwdThreads) {
-    const int r = i / (kTileX + 1), xx = i % (kTileX + 1);
-    int v = 0;
-    if (r < nrows) v = __ldg(vox_pt + rank0 + (int64_t)r * prm.x + min(xx, w));
-    s_pt[r][xx] = v;
+  // sorted-point range of each tile row, then equal-size chunks (multiples of 32 points)
+  if (threadIdx.x < kTileRows) {
+    const int r = threadIdx.x;
+    int lo = 0, hi = 0;
+    if (r < nrows) {
+      lo = __ldg(vox_pt + rank0 + (int64_t)r * prm.x);
+      hi = __ldg(vox_pt + rank0 + (int64_t)r * prm.x + w);
+    }
+    s_row_lo[r] = lo;
+    s_row_hi[r] = hi;
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int total = 0;
+    for (int r = 0; r < kTileRows; ++r) total += s_row_hi[r] - s_row_lo[r];
+    const int target = max(1, n_warps * prm.chunks_per_warp);
+    int chunk = ((total + target - 1) / target + 31) & ~31;
+    if (chunk < 32) chunk = 32;
+    int items = 0;
+    for (int r = 0; r < kTileRows; ++r) {
+      s_item0[r] = items;
+      items += (s_row_hi[r] - s_row_lo[r] + chunk - 1) / chunk;
+    }
+    s_item0[kTileRows] = items;
+    s_chunk = chunk;
+  }
+  __syncthreads();
+  const int chunk = s_chunk, n_items = s_item0[kTileRows];
 
   for (int cb = 0; cb < c4; cb += 32) {   // one sweep when C <= 128
     const bool act = cb + lane < c4;
     const int cw = min(prm.c - 4 * cb, 128);
-    for (int i = threadIdx.x; i < cw * kTileStride; i += kFwdThreads) tile[i] = 0.f;
+    float* tile = smem;
+    float* part = smem + cw * kTileStride;
+    const T* feat_lane = feat + 4 * (cb + min(lane, c4 - 1 - cb));
+    for (int i = threadIdx.x; i < cw * kTileStride; i += n_threads) tile[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * kMaxItems; i += n_threads) (&s_col[0][0])[i] = -1;
     if (threadIdx.x == 0) s_next = 0;
     __syncthreads();
 
-    // ---- phase 1: 8-voxel groups, grabbed dynamically; long voxels are left for phase 2
-    bool any_long = false;
-    const int groups_per_row = (w + kGroup - 1) / kGroup;
-    const int n_items = nrows * groups_per_row;
+    // ---- phase 1: chunks grabbed dynamically
     for (;;) {
       int item = 0;
       if (lane == 0) item = atomicAdd(&s_next, 1);
       item = __shfl_sync(kFullMask, item, 0);
       if (item >= n_items) break;
-      const int r = item / groups_per_row, g = item % groups_per_row;
-      const int xb = g * kGroup, xe = min(w, xb + kGroup);
-      const int* row_pt = s_pt[r];
-      int xv = xb;
-      while (xv < xe) {
-        if (row_pt[xv + 1] - row_pt[xv] > kLongVoxel) { any_long = true; ++xv; continue; }
-        const int xs = xv;
-        while (xv < xe && row_pt[xv + 1] - row_pt[xv] <= kLongVoxel) ++xv;
-        // skip leading empty voxels so `cur` always names the voxel of the first point
-        int cur = xs;
-        while (cur < xv && row_pt[cur + 1] == row_pt[xs]) ++cur;
-        if (cur < xv)
-          flat_sum<T, true>(depth, feat, rd, rf, row_pt[xs], row_pt[xv], prm, c4, cb, act, row_pt, cur,
-                            tile + r * kTileX);
-      }
+      int r = 0;
+      while (item >= s_item0[r + 1]) ++r;
+      const int lo = s_row_lo[r], hi = s_row_hi[r];
+      const int p = lo + (item - s_item0[r]) * chunk, pe = min(hi, p + chunk);
+      // is the first / last voxel of the chunk shared with a neighbouring chunk?
+      const bool head_partial = p > lo && __ldg(rb + p - 1) == __ldg(rb + p);
+      const bool tail_partial = pe < hi && __ldg(rb + pe) == __ldg(rb + pe - 1);
+      chunk_sum<T>(depth, feat_lane, rd, rf, rb, p, pe, head_partial, tail_partial, prm,
+                   (int)(rank0 + (int64_t)r * prm.x), tile + (4 * lane) * kTileStride + r * kTileX,
+                   part + (size_t)item * 2 * cw + 4 * lane, s_col[item], cw, act);
     }
-    // ---- phase 2: long voxels, all warps split the point range; partials combined in warp order
-    if (__syncthreads_or(any_long)) {
-      for (int r = 0; r < nrows; ++r)
-        for (int xv = 0; xv < w; ++xv) {
-          const int s = s_pt[r][xv], len = s_pt[r][xv + 1] - s;
-          if (len <= kLongVoxel) continue;
-          const int per = ((len + kFwdWarps - 1) / kFwdWarps + 31) & ~31;
-          const int b = min(len, warp * per), e = min(len, b + per);
-          s_partial[warp][lane] = flat_sum<T, false>(depth, feat, rd, rf, (int64_t)s + b, (int64_t)s + e, prm, c4, cb,
-                                                     act, nullptr, 0, nullptr);
-          __syncthreads();
-          if (warp == 0 && act) {
-            float4 acc = s_partial[0][lane];
+    __syncthreads();
+    // ---- phase 2: add the cut voxels' partial sums in item order (fixed summation order)
+    for (int r = warp; r < nrows; r += n_warps) {
+      float* tile_lane = tile + (4 * lane) * kTileStride + r * kTileX;
+      for (int item = s_item0[r]; item < s_item0[r + 1]; ++item)
 #pragma unroll
-            for (int k = 1; k < kFwdWarps; ++k) {
-              const float4 q = s_partial[k][lane];
-              acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
-            }
-            float* col = tile + r * kTileX + xv;
-            col[(4 * lane + 0) * kTileStride] = acc.x;
-            col[(4 * lane + 1) * kTileStride] = acc.y;
-            col[(4 * lane + 2) * kTileStride] = acc.z;
-            col[(4 * lane + 3) * kTileStride] = acc.w;
+        for (int slot = 0; slot < 2; ++slot) {
+          const int col = s_col[item][slot];
+          if (col >= 0 && act) {
+            const float4 pv = *reinterpret_cast<const float4*>(part + ((size_t)item * 2 + slot) * cw + 4 * lane);
+            float* c = tile_lane + col;
+            c[0 * kTileStride] += pv.x;
+            c[1 * kTileStride] += pv.y;
+            c[2 * kTileStride] += pv.z;
+            c[3 * kTileStride] += pv.w;
           }
-          __syncthreads();
         }
     }
     __syncthreads();
 
-    // ---- write-out
+    // ---- write-out (no integer divisions here: they were a third of the kernel's instructions)
     if (LAYOUT == BEVPOOL_LAYOUT_BCZYX) {
       // out[((frame*C + ch)*rows + row0 + r)*X + x0 + lane]: one 128-byte row per warp store
-      const int64_t base = frame * prm.c * vpf + row0 * prm.x + x0 + lane;
-      for (int i = warp; i < cw * nrows; i += kFwdWarps) {
-        const int cc = i / nrows, r = i % nrows;
-        if (lane < w)
-          Vec4<T>::store1s(out, base + (int64_t)(4 * cb + cc) * vpf + (int64_t)r * prm.x,
-                           tile[cc * kTileStride + r * kTileX + lane]);
+      if (lane < w) {
+        for (int cc = warp; cc < cw; cc += n_warps) {
+          const int64_t o = frame * prm.c * vpf + (int64_t)(4 * cb + cc) * vpf + row0 * prm.x + x0 + lane;
+          const float* src = tile + cc * kTileStride + lane;
+#pragma unroll
+          for (int r = 0; r < kTileRows; ++r)
+            if (r < nrows) Vec4<T>::store1s(out, o + (int64_t)r * prm.x, src[r * kTileX]);
+        }
       }
     } else {
-      // out[(rank)*C + ch]: consecutive threads take consecutive channels of one voxel
-      for (int i = threadIdx.x; i < nrows * w * cw; i += kFwdThreads) {
-        const int cc = i % cw, col = i / cw;
-        const int r = col / w, xx = col % w;
-        Vec4<T>::store1s(out, (rank0 + (int64_t)r * prm.x + xx) * prm.c + 4 * cb + cc,
-                         tile[cc * kTileStride + r * kTileX + xx]);
-      }
+      // out[(rank)*C + ch]: a warp writes the channels of one voxel (coalesced), voxels striped over warps
+      for (int r = 0; r < nrows; ++r)
+        for (int xx = warp; xx < w; xx += n_warps) {
+          const int64_t o = (rank0 + (int64_t)r * prm.x + xx) * prm.c + 4 * cb;
+          for (int cc = lane; cc < cw; cc += 32) Vec4<T>::store1s(out, o + cc, tile[cc * kTileStride + r * kTileX + xx]);
+        }
     }
     __syncthreads();
   }
@@ -292,154 +344,189 @@ pool_bwd_block_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
                       const int* __restrict__ point_rank, BwdParams prm, T* __restrict__ depth_grad,
                       T* __restrict__ feat_grad) {
   extern __shared__ unsigned char smem_raw[];
-  int* s_rank = reinterpret_cast<int*>(smem_raw);                                  // [d][32]
-  float* s_depth = reinterpret_cast<float*>(smem_raw) + (size_t)prm.d * kPixBlock;  // [d][32]
-  float* s_dg = s_depth + (size_t)prm.d * kPixBlock;                                // [d][32]
-  float* s_fg = s_dg + (size_t)prm.d * kPixBlock;                                   // [cw][33] (NCHW output only)
+  // [d][32] each: voxel rank, depth, depth_grad of the block; then per-warp compacted point lists
+  int* s_rank = reinterpret_cast<int*>(smem_raw);
+  float* s_depth = reinterpret_cast<float*>(smem_raw) + (size_t)prm.d * kPixBlock;
+  float* s_dg = s_depth + (size_t)prm.d * kPixBlock;
+  int4* s_list = reinterpret_cast<int4*>(s_dg + (size_t)prm.d * kPixBlock);            // [8 warps][d] {rank, depth, dbin, -}
+  float* s_fg = reinterpret_cast<float*>(s_list + (size_t)kBwdWarps * prm.d);           // [cw][33] (NCHW output only)
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const int c4 = prm.c >> 2;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 
   const int blk = blockIdx.x;
-  const int bn = blk / (prm.blocks_w * prm.blocks_h);
-  const int bh = (blk / prm.blocks_w) % prm.blocks_h, bw = blk % prm.blocks_w;
+  const int per_img = prm.blocks_w * prm.blocks_h;
+  const int bn = blk / per_img;
+  const int brem = blk - bn * per_img;
+  const int bh = brem / prm.blocks_w, bw = brem - bh * prm.blocks_w;
   const int h0 = bh * kPixH, w0 = bw * kPixW;
   const int64_t hw = (int64_t)prm.h * prm.w;
   const int64_t img_base = (int64_t)bn * prm.d * hw;   // + d*hw + h*W + w
 
   // ---- stage point_rank / depth of the block: 8 consecutive w = one 32-byte sector per (d, h)
-  for (int i = threadIdx.x; i < prm.d * kPixBlock; i += kBwdThreads) {
-    const int dd = i / kPixBlock, px = i % kPixBlock;
-    const int hh = h0 + px / kPixW, ww = w0 + px % kPixW;
-    int r = -1;
-    float dv = 0.f;
-    if (hh < prm.h && ww < prm.w) {
-      const int64_t o = img_base + (int64_t)dd * hw + (int64_t)hh * prm.w + ww;
-      r = ldg_stream_i32(point_rank + o);
-      if (r >= 0) dv = Vec4<T>::load1(depth, o);
+  {
+    const int px = threadIdx.x & 31;
+    const int hh = h0 + (px >> 3), ww = w0 + (px & 7);
+    const bool in = hh < prm.h && ww < prm.w;
+    const int64_t o0 = img_base + (int64_t)hh * prm.w + ww;
+    for (int dd = threadIdx.x >> 5; dd < prm.d; dd += kBwdWarps) {
+      int r = -1;
+      float dv = 0.f;
+      if (in) {
+        r = ldg_stream_i32(point_rank + o0 + dd * hw);
+        if (r >= 0) dv = Vec4<T>::load1(depth, o0 + dd * hw);
+      }
+      s_rank[dd * kPixBlock + px] = r;
+      s_depth[dd * kPixBlock + px] = dv;
+      s_dg[dd * kPixBlock + px] = 0.f;
     }
-    s_rank[i] = r;
-    s_depth[i] = dv;
-    s_dg[i] = 0.f;
   }
   __syncthreads();
 
+  int4* my_list = s_list + (size_t)warp * prm.d;
   for (int cb = 0; cb < c4; cb += 32) {
     const bool act = cb + lane < c4;
     const int cw = min(prm.c - 4 * cb, 128);
+    const int lane_c = 4 * (cb + min(lane, c4 - 1 - cb));     // idle lanes alias the last chunk; never stored
+    const T* og_lane = og + lane_c;
     for (int px = warp; px < kPixBlock; px += kBwdWarps) {
-      const int hh = h0 + px / kPixW, ww = w0 + px % kPixW;
+      const int hh = h0 + (px >> 3), ww = w0 + (px & 7);
       if (hh >= prm.h || ww >= prm.w) continue;   // warp-uniform
       const int64_t pix = (int64_t)bn * hw + (int64_t)hh * prm.w + ww;
-      const float4 fv = act ? Vec4<T>::load(feat, pix * prm.c + 4 * (cb + lane)) : zero;
-      float4 fg = zero;
+      // compact the kept depth bins of this pixel into the warp's list
+      int n_kept = 0;
       for (int d0 = 0; d0 < prm.d; d0 += 32) {
-        const int my_r = (d0 + lane < prm.d) ? s_rank[(d0 + lane) * kPixBlock + px] : -1;
-        unsigned live = __ballot_sync(kFullMask, my_r >= 0);
-        while (live) {
-          // next (up to) 8 kept depth bins of this pixel
-          int dsel[8];
-          float4 g[8];
-          float pr[8];
+        const int dd = d0 + lane;
+        const int r = dd < prm.d ? s_rank[dd * kPixBlock + px] : -1;
+        const unsigned live = __ballot_sync(kFullMask, r >= 0);
+        if (r >= 0)
+          my_list[n_kept + __popc(live & ((1u << lane) - 1u))] =
+              make_int4(r, __float_as_int(s_depth[dd * kPixBlock + px]), dd, 0);
+        n_kept += __popc(live);
+      }
+      __syncwarp();
+      const float4 fv = Vec4<T>::load(feat, pix * prm.c + lane_c);
+      float4 fg = zero;
+      for (int b = 0; b < n_kept; b += 8) {
+        float4 g[8];
+        float dv[8], pr[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            dsel[u] = live ? (__ffs(live) - 1) : -1;
-            live &= live - 1;   // 0 stays 0
+        for (int u = 0; u < 8; ++u) {
+          if (b + u < n_kept) {                     // warp-uniform
+            const int4 e = my_list[b + u];          // broadcast read
+            g[u] = Vec4<T>::load(og_lane, (int64_t)e.x * prm.c);
+            dv[u] = __int_as_float(e.y);
+          } else {
+            g[u] = zero;
+            dv[u] = 0.f;
           }
+        }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int r = __shfl_sync(kFullMask, my_r, dsel[u] < 0 ? 0 : dsel[u]);
-            g[u] = (act && dsel[u] >= 0) ? Vec4<T>::load(og, (int64_t)r * prm.c + 4 * (cb + lane)) : zero;
-          }
+        for (int u = 0; u < 8; ++u) {
+          fg = fma4(g[u], dv[u], fg);
+          pr[u] = act ? dot4_packed(g[u], fv) : 0.f;
+        }
+        // reduce-scatter over lane bits 2,1,0, then finish over bits 3,4: lane l ends up with the
+        // complete dot product of point b + (l & 7)
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float dv = dsel[u] >= 0 ? s_depth[(d0 + dsel[u]) * kPixBlock + px] : 0.f;
-            fg = fma4(g[u], dv, fg);
-            pr[u] = dot4(g[u], fv, 0.f);
-          }
-          // reduce-scatter over lane bits 2,1,0, then finish over bits 3,4: lane l ends up with the
-          // complete dot product of point (l & 7)
+        for (int u = 0; u < 4; ++u) {
+          const float mine = (lane & 4) ? pr[u + 4] : pr[u];
+          const float send = (lane & 4) ? pr[u] : pr[u + 4];
+          pr[u] = mine + __shfl_xor_sync(kFullMask, send, 4);
+        }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float mine = (lane & 4) ? pr[u + 4] : pr[u];
-            const float send = (lane & 4) ? pr[u] : pr[u + 4];
-            pr[u] = mine + __shfl_xor_sync(kFullMask, send, 4);
-          }
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const float mine = (lane & 2) ? pr[u + 2] : pr[u];
-            const float send = (lane & 2) ? pr[u] : pr[u + 2];
-            pr[u] = mine + __shfl_xor_sync(kFullMask, send, 2);
-          }
-          {
-            const float mine = (lane & 1) ? pr[1] : pr[0];
-            const float send = (lane & 1) ? pr[0] : pr[1];
-            pr[0] = mine + __shfl_xor_sync(kFullMask, send, 1);
-          }
-          pr[0] += __shfl_xor_sync(kFullMask, pr[0], 8);
-          pr[0] += __shfl_xor_sync(kFullMask, pr[0], 16);
-          // lane u (< 8) publishes point u
-          int my_sel = dsel[0];
-#pragma unroll
-          for (int u = 1; u < 8; ++u) my_sel = (lane == u) ? dsel[u] : my_sel;
-          if (lane < 8 && my_sel >= 0) {
-            float* slot = s_dg + (d0 + my_sel) * kPixBlock + px;
-            *slot = (cb == 0) ? pr[0] : *slot + pr[0];
-          }
+        for (int u = 0; u < 2; ++u) {
+          const float mine = (lane & 2) ? pr[u + 2] : pr[u];
+          const float send = (lane & 2) ? pr[u] : pr[u + 2];
+          pr[u] = mine + __shfl_xor_sync(kFullMask, send, 2);
+        }
+        {
+          const float mine = (lane & 1) ? pr[1] : pr[0];
+          const float send = (lane & 1) ? pr[0] : pr[1];
+          pr[0] = mine + __shfl_xor_sync(kFullMask, send, 1);
+        }
+        pr[0] += __shfl_xor_sync(kFullMask, pr[0], 8);
+        pr[0] += __shfl_xor_sync(kFullMask, pr[0], 16);
+        if (lane < 8 && b + lane < n_kept) {
+          float* slot = s_dg + my_list[b + lane].z * kPixBlock + px;
+          *slot = (cb == 0) ? pr[0] : *slot + pr[0];
         }
       }
+      __syncwarp();
       if (prm.feat_grad_nchw) {
         if (act) {
-          s_fg[(4 * lane + 0) * (kPixBlock + 1) + px] = fg.x;
-          s_fg[(4 * lane + 1) * (kPixBlock + 1) + px] = fg.y;
-          s_fg[(4 * lane + 2) * (kPixBlock + 1) + px] = fg.z;
-          s_fg[(4 * lane + 3) * (kPixBlock + 1) + px] = fg.w;
+          float* c = s_fg + (4 * lane) * (kPixBlock + 1) + px;
+          c[0 * (kPixBlock + 1)] = fg.x;
+          c[1 * (kPixBlock + 1)] = fg.y;
+          c[2 * (kPixBlock + 1)] = fg.z;
+          c[3 * (kPixBlock + 1)] = fg.w;
         }
       } else if (act) {
-        Vec4<T>::store(feat_grad, pix * prm.c + 4 * (cb + lane), fg);
+        Vec4<T>::store(feat_grad, pix * prm.c + lane_c, fg);
       }
     }
     if (prm.feat_grad_nchw) {
       __syncthreads();
       // feat_grad[bn][ch][h][w]: 8 consecutive w per (ch, h) = one sector
-      for (int i = threadIdx.x; i < cw * kPixBlock; i += kBwdThreads) {
-        const int cc = i / kPixBlock, px = i % kPixBlock;
-        const int hh = h0 + px / kPixW, ww = w0 + px % kPixW;
-        if (hh < prm.h && ww < prm.w)
-          Vec4<T>::store1s(feat_grad, ((int64_t)bn * prm.c + 4 * cb + cc) * hw + (int64_t)hh * prm.w + ww,
-                           s_fg[cc * (kPixBlock + 1) + px]);
+      const int px = threadIdx.x & 31;
+      const int hh = h0 + (px >> 3), ww = w0 + (px & 7);
+      if (hh < prm.h && ww < prm.w) {
+        const int64_t o0 = ((int64_t)bn * prm.c + 4 * cb) * hw + (int64_t)hh * prm.w + ww;
+        for (int cc = threadIdx.x >> 5; cc < cw; cc += kBwdWarps)
+          Vec4<T>::store1s(feat_grad, o0 + cc * hw, s_fg[cc * (kPixBlock + 1) + px]);
       }
       __syncthreads();
     }
   }
   __syncthreads();
   // ---- depth_grad of the block, zeros for dropped points included
-  for (int i = threadIdx.x; i < prm.d * kPixBlock; i += kBwdThreads) {
-    const int dd = i / kPixBlock, px = i % kPixBlock;
-    const int hh = h0 + px / kPixW, ww = w0 + px % kPixW;
-    if (hh < prm.h && ww < prm.w)
-      Vec4<T>::store1s(depth_grad, img_base + (int64_t)dd * hw + (int64_t)hh * prm.w + ww, s_dg[i]);
+  {
+    const int px = threadIdx.x & 31;
+    const int hh = h0 + (px >> 3), ww = w0 + (px & 7);
+    if (hh < prm.h && ww < prm.w) {
+      const int64_t o0 = img_base + (int64_t)hh * prm.w + ww;
+      for (int dd = threadIdx.x >> 5; dd < prm.d; dd += kBwdWarps)
+        Vec4<T>::store1s(depth_grad, o0 + dd * hw, s_dg[dd * kPixBlock + px]);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------ host side
 template <typename T, int LAYOUT>
 static int forward_tile_t(const void* depth, const void* feat, void* out, const int* rd, const int* rf,
-                          const int* vox_pt, const FwdParams& prm, cudaStream_t st) {
+                          const int* rb, const int* vox_pt, const FwdParams& prm, cudaStream_t st) {
   const int tiles_x = (prm.x + kTileX - 1) / kTileX;
   const int64_t tiles_per_frame = (int64_t)tiles_x * ((prm.rows + kTileRows - 1) / kTileRows);
   const int64_t n_tiles = tiles_per_frame * prm.frames;
   if (n_tiles == 0) return 0;
   if (n_tiles > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
   const int cw = prm.c < 128 ? prm.c : 128;
-  const size_t smem = sizeof(float) * (size_t)cw * kTileStride;
-  auto kern = pool_fwd_tile_kernel<T, LAYOUT>;
+  static int minb = 0;
+  if (!minb) {
+    const char* e = getenv("BEVPOOL_FWD_MINB");
+    minb = e ? atoi(e) : 2;
+  }
+  auto kern = minb >= 2 ? pool_fwd_tile_kernel<T, LAYOUT, 2> : pool_fwd_tile_kernel<T, LAYOUT, 1>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 128 * kTileStride));
+    const int max_smem = (int)(sizeof(float) * (128 * kTileStride + kMaxItems * 2 * 128));
+    cudaFuncSetAttribute(pool_fwd_tile_kernel<T, LAYOUT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(pool_fwd_tile_kernel<T, LAYOUT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     attr_set = true;
   }
-  kern<<<(unsigned)n_tiles, kFwdThreads, smem, st>>>((const T*)depth, (const T*)feat, (T*)out, rd, rf, vox_pt, prm,
+  static int warps = 0, cpw = 0;
+  if (!warps) {  // tuning knobs (defaults are the measured best on B200)
+    const char* e;
+    warps = (e = getenv("BEVPOOL_FWD_WARPS")) ? atoi(e) : 16;
+    cpw = (e = getenv("BEVPOOL_FWD_CPW")) ? atoi(e) : 1;
+    if (warps < 1 || warps > kFwdMaxWarps) warps = 8;
+    if (cpw < 1 || cpw > 2) cpw = 2;
+  }
+  FwdParams prm2 = prm;
+  prm2.chunks_per_warp = cpw;
+  const size_t smem = sizeof(float) * ((size_t)cw * kTileStride + (size_t)(warps * cpw + kTileRows) * 2 * cw);
+  const int kFwdThreads = warps * 32;
+  kern<<<(unsigned)n_tiles, kFwdThreads, smem, st>>>((const T*)depth, (const T*)feat, (T*)out, rd, rf, rb, vox_pt, prm2,
                                                       tiles_x, tiles_per_frame);
   count_launch();
   return launch_status();
@@ -454,7 +541,8 @@ static int backward_block_t(const void* og, void* dg, void* fg, const void* dept
   if (n_blocks == 0) return 0;
   if (n_blocks > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
   const int cw = prm.c < 128 ? prm.c : 128;
-  const size_t smem = sizeof(float) * ((size_t)3 * prm.d * kPixBlock + (prm.feat_grad_nchw ? (size_t)cw * (kPixBlock + 1) : 0));
+  const size_t smem = sizeof(float) * ((size_t)3 * prm.d * kPixBlock + (prm.feat_grad_nchw ? (size_t)cw * (kPixBlock + 1) : 0)) +
+                      sizeof(int4) * (size_t)kBwdWarps * prm.d;
   if (smem > 200 * 1024) return BEVPOOL_ERR_BAD_ARG;   // D > ~500 depth bins
   auto kern = pool_bwd_block_kernel<T>;
   static size_t attr = 0;
@@ -486,14 +574,15 @@ extern "C" int bevpool_voxel_table(const int32_t* ranks_bev_sorted, int64_t n_po
 }
 
 extern "C" int bevpool_v2_forward_dense(const void* depth, const void* feat, void* out, const int32_t* ranks_depth,
-                                        const int32_t* ranks_feat, const int32_t* vox_pt, int c, int64_t n_frames,
+                                        const int32_t* ranks_feat, const int32_t* ranks_bev, const int32_t* vox_pt,
+                                        int c, int64_t n_frames,
                                         int64_t rows_per_frame, int x, int dhw, int hw, int layout, int dtype,
                                         void* stream) {
   if (n_frames < 0 || rows_per_frame < 0 || x < 0) return BEVPOOL_ERR_BAD_ARG;
   if (c <= 0 || c % 4) return BEVPOOL_ERR_BAD_CHANNELS;
   if (n_frames * rows_per_frame * x == 0) return BEVPOOL_OK;
   if (n_frames * rows_per_frame * x >= INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
-  if (!depth || !feat || !out || !ranks_depth || !vox_pt) return BEVPOOL_ERR_BAD_ARG;
+  if (!depth || !feat || !out || !ranks_depth || !ranks_bev || !vox_pt) return BEVPOOL_ERR_BAD_ARG;
   if (!ranks_feat && (dhw <= 0 || hw <= 0)) return BEVPOOL_ERR_BAD_ARG;
   if (layout != BEVPOOL_LAYOUT_BZYXC && layout != BEVPOOL_LAYOUT_BCZYX) return BEVPOOL_ERR_BAD_ARG;
   if ((uintptr_t)feat % 16) return BEVPOOL_ERR_BAD_ARG;
@@ -502,10 +591,16 @@ extern "C" int bevpool_v2_forward_dense(const void* depth, const void* feat, voi
   prm.x = x;
   prm.rows = rows_per_frame;
   prm.frames = n_frames;
-  prm.dhw = dhw;
-  prm.hw = hw;
+  prm.dhw = dhw > 0 ? dhw : 1;
+  prm.hw = hw > 0 ? hw : 1;
+  {  // rd / dhw == (rd * mul) >> shift for 0 <= rd < 2^31 (round-up magic number)
+    int s = 0;
+    while (((int64_t)1 << s) < prm.dhw) ++s;
+    prm.dhw_shift = 31 + s;
+    prm.dhw_mul = (uint32_t)((((uint64_t)1 << (31 + s)) / (uint64_t)prm.dhw) + 1);
+  }
   cudaStream_t st = (cudaStream_t)stream;
-#define DISPATCH(T, L) return forward_tile_t<T, L>(depth, feat, out, ranks_depth, ranks_feat, vox_pt, prm, st)
+#define DISPATCH(T, L) return forward_tile_t<T, L>(depth, feat, out, ranks_depth, ranks_feat, ranks_bev, vox_pt, prm, st)
   if (dtype == BEVPOOL_F32) {
     if (layout == BEVPOOL_LAYOUT_BCZYX) DISPATCH(float, BEVPOOL_LAYOUT_BCZYX);
     DISPATCH(float, BEVPOOL_LAYOUT_BZYXC);

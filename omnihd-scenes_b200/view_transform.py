@@ -168,7 +168,7 @@ class _FusedViewPool(torch.autograd.Function):
         _launch_transpose(feat, feat_cl, pr.bn, C, pr.hw, True)           # [BN,C,HW] -> [BN,HW,C]
         vox_pt = _launch_voxel_table(pr.rb, pr.p0, pr.counts, B * Z * Y * X)
         out = feat.new_empty((B, C, Z, Y, X))
-        _launch_forward_dense(depth, feat_cl, out, pr.rd, None, vox_pt, B, Z * Y, X, _lib.LAYOUT_BCZYX,
+        _launch_forward_dense(depth, feat_cl, out, pr.rd, None, pr.rb, vox_pt, B, Z * Y, X, _lib.LAYOUT_BCZYX,
                               dhw=pr.d * pr.hw, hw=pr.hw)
         ctx.prepared, ctx.shape, ctx.feat_shape = pr, shape, feat.shape
         ctx.save_for_backward(depth, feat_cl)
