@@ -201,6 +201,15 @@ __device__ __forceinline__ void chunk_sum(const T* __restrict__ depth, const T* 
   flush(true);
 }
 
+// optional per-CTA timeline (debug builds of the bench only): {tile, smid, t_start, t_end} in ns
+__device__ unsigned long long g_fwd_timeline[8 * 8192];
+__device__ int g_fwd_timeline_on = 0;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 template <typename T, int LAYOUT, int MINB>
 __global__ void __launch_bounds__(kFwdMaxWarps * 32, MINB)
 pool_fwd_tile_kernel(const T* __restrict__ depth, const T* __restrict__ feat, T* __restrict__ out,
@@ -215,6 +224,8 @@ pool_fwd_tile_kernel(const T* __restrict__ depth, const T* __restrict__ feat, T*
   const int c4 = prm.c >> 2;
 
   const int64_t t = blockIdx.x;
+  unsigned long long t_start = 0;
+  if (g_fwd_timeline_on && threadIdx.x == 0) t_start = globaltimer_ns();
   const int64_t frame = t / tiles_per_frame;
   const int64_t tr = (t % tiles_per_frame) / tiles_x;   // tile row
   const int tx = (int)(t % tiles_x);
@@ -253,6 +264,8 @@ pool_fwd_tile_kernel(const T* __restrict__ depth, const T* __restrict__ feat, T*
   }
   __syncthreads();
   const int chunk = s_chunk, n_items = s_item0[kTileRows];
+  unsigned long long t_a = 0, t_b = 0, t_c = 0, t_d = 0;
+  if (g_fwd_timeline_on && threadIdx.x == 0) t_a = globaltimer_ns();
 
   for (int cb = 0; cb < c4; cb += 32) {   // one sweep when C <= 128
     const bool act = cb + lane < c4;
@@ -264,6 +277,7 @@ pool_fwd_tile_kernel(const T* __restrict__ depth, const T* __restrict__ feat, T*
     for (int i = threadIdx.x; i < 2 * kMaxItems; i += n_threads) (&s_col[0][0])[i] = -1;
     if (threadIdx.x == 0) s_next = 0;
     __syncthreads();
+    if (g_fwd_timeline_on && threadIdx.x == 0) t_b = globaltimer_ns();
 
     // ---- phase 1: chunks grabbed dynamically
     for (;;) {
@@ -283,6 +297,7 @@ pool_fwd_tile_kernel(const T* __restrict__ depth, const T* __restrict__ feat, T*
                    part + (size_t)item * 2 * cw + 4 * lane, s_col[item], cw, act);
     }
     __syncthreads();
+    if (g_fwd_timeline_on && threadIdx.x == 0) t_c = globaltimer_ns();
     // ---- phase 2: add the cut voxels' partial sums in item order (fixed summation order)
     for (int r = warp; r < nrows; r += n_warps) {
       float* tile_lane = tile + (4 * lane) * kTileStride + r * kTileX;
@@ -301,6 +316,7 @@ pool_fwd_tile_kernel(const T* __restrict__ depth, const T* __restrict__ feat, T*
         }
     }
     __syncthreads();
+    if (g_fwd_timeline_on && threadIdx.x == 0) t_d = globaltimer_ns();
 
     // ---- write-out (no integer divisions here: they were a third of the kernel's instructions)
     if (LAYOUT == BEVPOOL_LAYOUT_BCZYX) {
@@ -323,6 +339,19 @@ pool_fwd_tile_kernel(const T* __restrict__ depth, const T* __restrict__ feat, T*
         }
     }
     __syncthreads();
+  }
+  if (g_fwd_timeline_on && threadIdx.x == 0 && t < 8192) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    g_fwd_timeline[8 * t + 0] = (unsigned long long)(s_row_hi[0] - s_row_lo[0] + s_row_hi[1] - s_row_lo[1] +
+                                                     s_row_hi[2] - s_row_lo[2] + s_row_hi[3] - s_row_lo[3]);
+    g_fwd_timeline[8 * t + 1] = smid;
+    g_fwd_timeline[8 * t + 2] = t_start;
+    g_fwd_timeline[8 * t + 3] = globaltimer_ns();
+    g_fwd_timeline[8 * t + 4] = t_a;
+    g_fwd_timeline[8 * t + 5] = t_b;
+    g_fwd_timeline[8 * t + 6] = t_c;
+    g_fwd_timeline[8 * t + 7] = t_d;
   }
 }
 
@@ -635,4 +664,12 @@ extern "C" int bevpool_v2_backward_dense(const void* out_grad, void* depth_grad,
   if (dtype == BEVPOOL_BF16)
     return backward_block_t<__nv_bfloat16>(out_grad, depth_grad, feat_grad, depth, feat, point_rank, prm, st);
   return BEVPOOL_ERR_BAD_ARG;
+}
+
+// debug: enable / fetch the forward kernel's per-CTA timeline (not part of the public header)
+extern "C" int bevpool_debug_fwd_timeline(int enable, unsigned long long* host_out, int n_tiles) {
+  cudaMemcpyToSymbol(g_fwd_timeline_on, &enable, sizeof(int));
+  if (host_out && n_tiles > 0)
+    cudaMemcpyFromSymbol(host_out, g_fwd_timeline, sizeof(unsigned long long) * 8 * (n_tiles < 8192 ? n_tiles : 8192));
+  return (int)cudaGetLastError();
 }
