@@ -214,7 +214,7 @@ def run_native_arm(args):
 
     # measured P, I of set 0 (reported with the result; they depend on the camera ring)
     pr = pkg.view_transform._prepare_device(None, view.frustum, sets[0]["rots"], sets[0]["trans"], B, N, D, H, W,
-                                            view.dx, view.bx, view.nx, dev)
+                                            view.dx, view.bx, view.nx, dev, want_intervals=False)
     P, I = (int(v) for v in pr.counts.tolist())
     e = 2 if dt_t == torch.bfloat16 else 4
     ab = algorithmic_bytes(P0, P, I, F, V, C, e)
@@ -279,7 +279,7 @@ def run_native_arm(args):
     if rank == 0:
         bp = pkg.bev_pool
         prs = [pkg.view_transform._prepare_device(None, view.frustum, s["rots"], s["trans"], B, N, D, H, W,
-                                                  view.dx, view.bx, view.nx, dev) for s in sets]
+                                                  view.dx, view.bx, view.nx, dev, want_intervals=False) for s in sets]
         feats = [s["feat"].detach() for s in sets]                                    # [B,N,C,H,W]
         feat_cl = [f.new_empty((B * N, H, W, C)) for f in feats]
         for f, fc in zip(feats, feat_cl):
@@ -320,7 +320,7 @@ def run_native_arm(args):
         def k_prep(i):
             k = i % N_BUFFER_SETS
             pkg.view_transform._prepare_device(None, view.frustum, sets[k]["rots"], sets[k]["trans"], B, N, D, H, W,
-                                               view.dx, view.bx, view.nx, dev)
+                                               view.dx, view.bx, view.nx, dev, want_intervals=False)
 
         reps = 40
         for name, fn in (("pool_fwd_dense", k_fwd), ("grid_transpose", k_tr), ("pool_bwd_dense", k_bwd),

@@ -2,16 +2,22 @@
 // voxel_pooling_prepare_v2, plus the backward regrouping by ranks_feat — all on the device,
 // no host synchronisation, bit-exact against the reference's CPU results.
 //
-// Pipeline of bevpool_prepare_v2 (one stream, 2 + n_passes + 2 kernels):
-//   memset(zero region)                       histograms, look-back status words, tickets
-//   point_rank_kernel      P0 threads         geometry (optional) -> voxel rank | -1, digit
-//                                             histograms of every pass, kept-point count
-//   radix_scatter_kernel   x n_passes         one-sweep stable scatter: warp-level match ranking,
-//                                             decoupled look-back across tiles; the first pass
-//                                             also compacts (dropped points are never written)
-//   segment_heads_kernel   P threads          head flags (ballot) + scan -> interval_starts,
-//                                             ranks_feat derived from ranks_depth
-//   interval_lengths_kernel                   adjacent difference of starts
+// Pipeline of bevpool_prepare_v2 (one stream):
+//   memset(zero region)                 digit totals, next-pass tile histograms
+//   point_rank_kernel    P0 threads     geometry (optional) -> voxel rank | -1 per frustum point; the CTA
+//                                       is one sort tile, so it also emits the tile's pass-0 digit
+//                                       histogram, the digit totals of every pass and the kept count
+//   per pass:  tile_scan_kernel         exclusive scan of the tile histograms along tiles (one CTA per digit)
+//              radix_scatter_kernel     stable scatter: warp-level match ranking inside the tile + scanned
+//                                       tile offsets; pass 0 also compacts (dropped points are never
+//                                       written); each pass builds the next pass's tile histograms with
+//                                       fire-and-forget REDs at the destination positions
+//   (API path only) head_count / head_scan / head_write / interval_lengths: run-length segmentation by
+//                                       counted head flags and a scan, ranks_feat derived from ranks_depth
+//
+// There is no inter-CTA waiting anywhere (an earlier decoupled-look-back version serialised on chains of
+// ~500 predecessor tiles at these problem sizes: 23 us per pass; see profiles/). Sort tiles scale with the
+// input (2048 * rounds keys) so the per-tile tables stay small at 3.7e8 points.
 //
 // Exactness (SURVEY.md §7 hard part 3): the voxel index is trunc((coor - lo) / dx) with an IEEE
 // fp32 subtract and divide (__fsub_rn / __fdiv_rn; no reciprocal, no FMA), the geometry is
@@ -23,28 +29,33 @@ namespace bevpool {
 
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortItems = 8;                          // keys per thread
-constexpr int kSortTile = kSortThreads * kSortItems;   // keys per CTA
-constexpr int kRadixBits = 8;
-constexpr int kRadixBins = 1 << kRadixBits;
+constexpr int kSortItems = 8;                          // keys per thread and round
+constexpr int kSortRound = kSortThreads * kSortItems;  // keys per CTA and round
+constexpr int kMaxRadixBits = 9;
+constexpr int kMaxBins = 1 << kMaxRadixBits;
 constexpr int kMaxPasses = 4;
+constexpr int kMaxTiles = 4096;                        // tile tables are scanned by one CTA per digit
 
 constexpr int kHeadThreads = 256;
 constexpr int kHeadItems = 4;
-constexpr int kHeadTile = kHeadThreads * kHeadItems;
+constexpr int kHeadRound = kHeadThreads * kHeadItems;
 
 struct SortPlan {
   int n_passes;
   int shift[kMaxPasses];
   int bits[kMaxPasses];
+  int rounds;          // 2048-key rounds per sort tile
+  int64_t n_tiles;     // tiles covering the (uncompacted) input
+  int head_rounds;     // 1024-key rounds per segmentation tile
+  int64_t head_tiles;
 };
 
-static SortPlan make_plan(int64_t max_key) {
+static SortPlan make_plan(int64_t max_key, int64_t n_max) {
   int total_bits = 1;
   while (total_bits < 31 && ((int64_t)1 << total_bits) <= max_key) ++total_bits;
   SortPlan p;
-  p.n_passes = (total_bits + kRadixBits - 1) / kRadixBits;
-  // spread the bits evenly over the passes (e.g. 17 bits -> 6+6+5)
+  p.n_passes = (total_bits + kMaxRadixBits - 1) / kMaxRadixBits;
+  // spread the bits evenly over the passes (e.g. 17 bits -> 9+8)
   int left = total_bits, shift = 0;
   for (int i = 0; i < p.n_passes; ++i) {
     const int b = (left + (p.n_passes - i) - 1) / (p.n_passes - i);
@@ -54,6 +65,16 @@ static SortPlan make_plan(int64_t max_key) {
     left -= b;
   }
   for (int i = p.n_passes; i < kMaxPasses; ++i) p.shift[i] = p.bits[i] = 0;
+  const int64_t rounds_total = (n_max + kSortRound - 1) / kSortRound;
+  p.rounds = (int)((rounds_total + kMaxTiles - 1) / kMaxTiles);
+  if (p.rounds < 1) p.rounds = 1;
+  p.n_tiles = (rounds_total + p.rounds - 1) / p.rounds;
+  if (p.n_tiles < 1) p.n_tiles = 1;
+  const int64_t hr = (n_max + kHeadRound - 1) / kHeadRound;
+  p.head_rounds = (int)((hr + kMaxTiles - 1) / kMaxTiles);
+  if (p.head_rounds < 1) p.head_rounds = 1;
+  p.head_tiles = (hr + p.head_rounds - 1) / p.head_rounds;
+  if (p.head_tiles < 1) p.head_tiles = 1;
   return p;
 }
 
@@ -82,27 +103,13 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 }
 
 // ------------------------------------------------------------------------------------------ geometry
-struct Cam {
-  float r[9];
-  float t[3];
-};
-
-__device__ __forceinline__ void cam_point(const float* __restrict__ frustum, const Cam& cam, int64_t dhw,
-                                          float& x, float& y, float& z) {
+__device__ __forceinline__ void cam_point(const float* __restrict__ frustum, const float* cam /*R[9] t[3]*/,
+                                          int64_t dhw, float& x, float& y, float& z) {
   const float u = __ldg(frustum + 3 * dhw + 0), v = __ldg(frustum + 3 * dhw + 1), dd = __ldg(frustum + 3 * dhw + 2);
   const float px = __fmul_rn(u, dd), py = __fmul_rn(v, dd), pz = dd;
-  x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cam.r[0], px), __fmul_rn(cam.r[1], py)), __fmul_rn(cam.r[2], pz)), cam.t[0]);
-  y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cam.r[3], px), __fmul_rn(cam.r[4], py)), __fmul_rn(cam.r[5], pz)), cam.t[1]);
-  z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cam.r[6], px), __fmul_rn(cam.r[7], py)), __fmul_rn(cam.r[8], pz)), cam.t[2]);
-}
-
-__device__ __forceinline__ Cam load_cam(const float* __restrict__ rots, const float* __restrict__ trans, int64_t bn) {
-  Cam c;
-#pragma unroll
-  for (int i = 0; i < 9; ++i) c.r[i] = __ldg(rots + bn * 9 + i);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) c.t[i] = __ldg(trans + bn * 3 + i);
-  return c;
+  x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cam[0], px), __fmul_rn(cam[1], py)), __fmul_rn(cam[2], pz)), cam[9]);
+  y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cam[3], px), __fmul_rn(cam[4], py)), __fmul_rn(cam[5], pz)), cam[10]);
+  z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cam[6], px), __fmul_rn(cam[7], py)), __fmul_rn(cam[8], pz)), cam[11]);
 }
 
 // grid: (ceil(DHW / 256), BN): every CTA works inside one camera, so R|t are CTA-uniform
@@ -110,7 +117,11 @@ __global__ void __launch_bounds__(256)
 geometry_kernel(const float* __restrict__ frustum, const float* __restrict__ rots, const float* __restrict__ trans,
                 float* __restrict__ coor, int64_t dhw_total) {
   const int64_t bn = blockIdx.y;
-  const Cam cam = load_cam(rots, trans, bn);
+  float cam[12];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) cam[i] = __ldg(rots + bn * 9 + i);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) cam[9 + i] = __ldg(trans + bn * 3 + i);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < dhw_total; i += (int64_t)gridDim.x * blockDim.x) {
     float x, y, z;
     cam_point(frustum, cam, i, x, y, z);
@@ -123,8 +134,12 @@ geometry_kernel(const float* __restrict__ frustum, const float* __restrict__ rot
 
 // ------------------------------------------------------------------------------------------ voxel rank
 struct GridDev {
-  int64_t dhw;         // D*H*W
+  int64_t n_points;    // B*N*D*H*W
+  int dhw;             // D*H*W
+  uint32_t dhw_mul;    // idx / dhw == (idx * dhw_mul) >> dhw_shift for idx < 2^31
+  int dhw_shift;
   int n_cams;          // N
+  int bn;              // B*N
   int nx, ny, nz;
   float lo[3], dx[3];
 };
@@ -138,63 +153,82 @@ __device__ __forceinline__ bool voxel_index(float c, float lo, float dx, int n, 
   return t >= 0 && t < n;
 }
 
+// One CTA = one sort tile of the (uncompacted) point list: rank of every point, the tile's pass-0
+// digit histogram (tile_hist0[tile][bins0]), digit totals of all passes, kept count.
 template <bool FROM_COOR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kSortThreads)
 point_rank_kernel(const float* __restrict__ coor, const float* __restrict__ frustum, const float* __restrict__ rots,
                   const float* __restrict__ trans, GridDev g, SortPlan plan, int* __restrict__ point_rank,
-                  uint32_t* __restrict__ hist /*[kMaxPasses][256]*/, int* __restrict__ n_kept) {
-  __shared__ uint32_t sh[kMaxPasses][kRadixBins];
+                  uint32_t* __restrict__ tile_hist0, uint32_t* __restrict__ totals /*[kMaxPasses][kMaxBins]*/,
+                  int* __restrict__ n_kept) {
+  extern __shared__ float s_cam[];                       // [bn][12] (fused geometry only)
+  __shared__ uint32_t sh[kMaxPasses][kMaxBins];
   __shared__ uint32_t s_kept;
-  for (int i = threadIdx.x; i < kMaxPasses * kRadixBins; i += blockDim.x) (&sh[0][0])[i] = 0;
-  if (threadIdx.x == 0) s_kept = 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kMaxPasses * kMaxBins; i += kSortThreads) (&sh[0][0])[i] = 0;
+  if (tid == 0) s_kept = 0;
+  if (!FROM_COOR)
+    for (int i = tid; i < g.bn * 12; i += kSortThreads) {
+      const int c = i / 12, k = i - c * 12;
+      s_cam[i] = k < 9 ? __ldg(rots + c * 9 + k) : __ldg(trans + c * 3 + (k - 9));
+    }
   __syncthreads();
-  const int64_t bn = blockIdx.y;
-  const int64_t frame = bn / g.n_cams;
-  Cam cam;
-  if (!FROM_COOR) cam = load_cam(rots, trans, bn);
   const int64_t vpf = (int64_t)g.nx * g.ny * g.nz;
+  const int64_t tile_base = (int64_t)blockIdx.x * plan.rounds * kSortRound;
   uint32_t kept = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < g.dhw; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t idx = bn * g.dhw + i;
-    float x, y, z;
-    if (FROM_COOR) {
-      x = ldg_stream_f32(coor + 3 * idx + 0);
-      y = ldg_stream_f32(coor + 3 * idx + 1);
-      z = ldg_stream_f32(coor + 3 * idx + 2);
-    } else {
-      cam_point(frustum, cam, i, x, y, z);
-    }
-    int vx, vy, vz;
-    const bool ok = voxel_index(x, g.lo[0], g.dx[0], g.nx, vx) & voxel_index(y, g.lo[1], g.dx[1], g.ny, vy) &
-                    voxel_index(z, g.lo[2], g.dx[2], g.nz, vz);
-    int rank = -1;
-    if (ok) {
-      rank = (int)(frame * vpf + ((int64_t)vz * g.ny + vy) * g.nx + vx);
-      ++kept;
+  for (int r = 0; r < plan.rounds; ++r) {
+    const int64_t base = tile_base + (int64_t)r * kSortRound + warp * (32 * kSortItems) + lane;
+#pragma unroll 2
+    for (int j = 0; j < kSortItems; ++j) {
+      const int64_t idx = base + j * 32;
+      if (idx >= g.n_points) continue;
+      const int cam = (int)(((uint64_t)(uint32_t)idx * g.dhw_mul) >> g.dhw_shift);   // b*N + n
+      float x, y, z;
+      if (FROM_COOR) {
+        x = ldg_stream_f32(coor + 3 * idx + 0);
+        y = ldg_stream_f32(coor + 3 * idx + 1);
+        z = ldg_stream_f32(coor + 3 * idx + 2);
+      } else {
+        cam_point(frustum, s_cam + cam * 12, idx - (int64_t)cam * g.dhw, x, y, z);
+      }
+      int vx, vy, vz;
+      const bool ok = voxel_index(x, g.lo[0], g.dx[0], g.nx, vx) & voxel_index(y, g.lo[1], g.dx[1], g.ny, vy) &
+                      voxel_index(z, g.lo[2], g.dx[2], g.nz, vz);
+      int rank = -1;
+      if (ok) {
+        rank = (int)((int64_t)(cam / g.n_cams) * vpf + ((int64_t)vz * g.ny + vy) * g.nx + vx);
+        ++kept;
 #pragma unroll
-      for (int p = 0; p < kMaxPasses; ++p)
-        if (p < plan.n_passes) atomicAdd(&sh[p][(rank >> plan.shift[p]) & ((1 << plan.bits[p]) - 1)], 1u);
+        for (int p = 0; p < kMaxPasses; ++p)
+          if (p < plan.n_passes) atomicAdd(&sh[p][(rank >> plan.shift[p]) & ((1 << plan.bits[p]) - 1)], 1u);
+      }
+      point_rank[idx] = rank;
     }
-    point_rank[idx] = rank;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(kFullMask, kept, o);
-  if (lane_id() == 0 && kept) atomicAdd(&s_kept, kept);
+  if (lane == 0 && kept) atomicAdd(&s_kept, kept);
   __syncthreads();
-  for (int i = threadIdx.x; i < plan.n_passes * kRadixBins; i += blockDim.x) {
+  const int bins0 = 1 << plan.bits[0];
+  for (int d = tid; d < bins0; d += kSortThreads) tile_hist0[(int64_t)blockIdx.x * bins0 + d] = sh[0][d];
+  for (int i = tid; i < plan.n_passes * kMaxBins; i += kSortThreads) {
     const uint32_t v = (&sh[0][0])[i];
-    if (v) atomicAdd(hist + i, v);
+    if (v) atomicAdd(totals + i, v);
   }
-  if (threadIdx.x == 0 && s_kept) atomicAdd(n_kept, (int)s_kept);
+  if (tid == 0 && s_kept) atomicAdd(n_kept, (int)s_kept);
 }
 
-// Digit histograms of every pass for an existing key array (backward regroup).
-__global__ void __launch_bounds__(256)
-key_hist_kernel(const int* __restrict__ keys, int64_t n, SortPlan plan, uint32_t* __restrict__ hist) {
-  __shared__ uint32_t sh[kMaxPasses][kRadixBins];
-  for (int i = threadIdx.x; i < kMaxPasses * kRadixBins; i += blockDim.x) (&sh[0][0])[i] = 0;
+// Same bookkeeping for an existing key array (backward regroup): tile histogram of pass 0 + totals.
+__global__ void __launch_bounds__(kSortThreads)
+key_hist_kernel(const int* __restrict__ keys, int64_t n, SortPlan plan, uint32_t* __restrict__ tile_hist0,
+                uint32_t* __restrict__ totals) {
+  __shared__ uint32_t sh[kMaxPasses][kMaxBins];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kMaxPasses * kMaxBins; i += kSortThreads) (&sh[0][0])[i] = 0;
   __syncthreads();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t tile_base = (int64_t)blockIdx.x * plan.rounds * kSortRound;
+  const int64_t tile_end = min(n, tile_base + (int64_t)plan.rounds * kSortRound);
+  for (int64_t i = tile_base + tid; i < tile_end; i += kSortThreads) {
     const int k = ldg_stream_i32(keys + i);
     if (k < 0) continue;
 #pragma unroll
@@ -202,164 +236,232 @@ key_hist_kernel(const int* __restrict__ keys, int64_t n, SortPlan plan, uint32_t
       if (p < plan.n_passes) atomicAdd(&sh[p][(k >> plan.shift[p]) & ((1 << plan.bits[p]) - 1)], 1u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < plan.n_passes * kRadixBins; i += blockDim.x) {
+  const int bins0 = 1 << plan.bits[0];
+  for (int d = tid; d < bins0; d += kSortThreads) tile_hist0[(int64_t)blockIdx.x * bins0 + d] = sh[0][d];
+  for (int i = tid; i < plan.n_passes * kMaxBins; i += kSortThreads) {
     const uint32_t v = (&sh[0][0])[i];
-    if (v) atomicAdd(hist + i, v);
+    if (v) atomicAdd(totals + i, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ tile scan
+// hist is [n_tiles][bins]; CTA d turns column d into its exclusive prefix along tiles (in place).
+__global__ void __launch_bounds__(256)
+tile_scan_kernel(uint32_t* __restrict__ hist, int64_t n_tiles, int bins) {
+  __shared__ uint32_t scan_tmp[8];
+  const int d = blockIdx.x;
+  uint32_t carry = 0;
+  for (int64_t t0 = 0; t0 < n_tiles; t0 += 256) {
+    const int64_t t = t0 + threadIdx.x;
+    const uint32_t v = t < n_tiles ? hist[t * bins + d] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan_256(v, scan_tmp, &total);
+    if (t < n_tiles) hist[t * bins + d] = carry + ex;
+    carry += total;
   }
 }
 
 // ------------------------------------------------------------------------------------------ radix pass
-// One stable LSD pass in a single sweep. Keys < 0 are dropped (first pass = compaction).
-// vals_in == nullptr means "value = position" (first pass of an argsort).
-// Tile order is handed out by an atomic ticket so look-back never waits on an unscheduled CTA.
+// One stable LSD pass. Keys < 0 are dropped (pass 0 = compaction). vals_in == nullptr means
+// "value = position" (first pass of an argsort). tile_prefix[tile][bins] holds, per digit, the number
+// of keys with that digit in earlier tiles. next_hist (optional): tile histograms of the NEXT pass,
+// accumulated at the destination positions.
 __global__ void __launch_bounds__(kSortThreads)
 radix_scatter_kernel(const int* __restrict__ keys_in, const int* __restrict__ vals_in, int* __restrict__ keys_out,
-                     int* __restrict__ vals_out, const uint32_t* __restrict__ digit_hist, uint32_t* __restrict__ status,
-                     uint32_t* __restrict__ ticket, const int* __restrict__ n_dev, int64_t n_host, int shift, int bits) {
-  __shared__ uint32_t warp_hist[kSortWarps][kRadixBins];
-  __shared__ uint32_t digit_base[kRadixBins];
+                     int* __restrict__ vals_out, const uint32_t* __restrict__ digit_totals,
+                     const uint32_t* __restrict__ tile_prefix, uint32_t* __restrict__ next_hist,
+                     const int* __restrict__ n_dev, int64_t n_host, int shift, int bits, int rounds, int next_shift,
+                     int next_bits) {
+  __shared__ uint32_t warp_hist[kSortWarps][kMaxBins];
+  __shared__ uint32_t digit_base[kMaxBins];
+  __shared__ uint32_t round_total[kMaxBins];
   __shared__ uint32_t scan_tmp[8];
-  __shared__ int s_tile;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bins = 1 << bits;
-  if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
-  for (int i = tid; i < kSortWarps * kRadixBins; i += kSortThreads) (&warp_hist[0][0])[i] = 0;
-  __syncthreads();
-  const int tile = s_tile;
   const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
-  const int64_t tile_base = (int64_t)tile * kSortTile;
+  const int64_t tile_keys = (int64_t)rounds * kSortRound;
+  const int64_t tile_base = (int64_t)blockIdx.x * tile_keys;
   if (tile_base >= n) return;
 
-  int key[kSortItems], val[kSortItems];
-  uint32_t rank[kSortItems];
-  const int64_t base = tile_base + warp * (32 * kSortItems) + lane;
-#pragma unroll
-  for (int j = 0; j < kSortItems; ++j) {
-    const int64_t idx = base + j * 32;
-    key[j] = idx < n ? ldg_stream_i32(keys_in + idx) : -1;
-    val[j] = vals_in ? (idx < n ? ldg_stream_i32(vals_in + idx) : 0) : (int)idx;
-  }
-  // warp-level ranking: lanes with the same digit find each other with match.any
-#pragma unroll
-  for (int j = 0; j < kSortItems; ++j) {
-    const bool valid = key[j] >= 0;
-    const int d = valid ? ((key[j] >> shift) & (bins - 1)) : bins;
-    const unsigned peers = __match_any_sync(kFullMask, d);
-    const int leader = __ffs(peers) - 1;
-    uint32_t b = 0;
-    if (valid && lane == leader) {
-      b = warp_hist[warp][d];
-      warp_hist[warp][d] = b + __popc(peers);
+  // digit_base = (keys with a smaller digit) + (keys with this digit in earlier tiles)
+  {
+    uint32_t carry = 0;
+    for (int d0 = 0; d0 < bins; d0 += kSortThreads) {
+      const int d = d0 + tid;
+      uint32_t total;
+      const uint32_t ex = block_exclusive_scan_256(d < bins ? __ldg(digit_totals + d) : 0u, scan_tmp, &total);
+      if (d < bins) digit_base[d] = carry + ex + __ldg(tile_prefix + (int64_t)blockIdx.x * bins + d);
+      carry += total;
     }
-    b = __shfl_sync(kFullMask, b, leader);
-    rank[j] = b + __popc(peers & ((1u << lane) - 1u));
-    __syncwarp();
   }
-  __syncthreads();
-  // exclusive scan of the global digit histogram (bins <= 256: one digit per thread)
-  uint32_t total;
-  const uint32_t digit_start = block_exclusive_scan_256(tid < bins ? __ldg(digit_hist + tid) : 0u, scan_tmp, &total);
-  if (tid < bins) {
-    uint32_t run = 0;
+  const uint32_t next_mask = (1u << next_bits) - 1u;
+  for (int r = 0; r < rounds; ++r) {
+    const int64_t round_base = tile_base + (int64_t)r * kSortRound;
+    if (round_base >= n) break;   // CTA-uniform
+    for (int w = 0; w < kSortWarps; ++w)
+      for (int d = tid; d < bins; d += kSortThreads) warp_hist[w][d] = 0;
+    __syncthreads();
+    int key[kSortItems], val[kSortItems];
+    uint32_t rank[kSortItems];
+    const int64_t base = round_base + warp * (32 * kSortItems) + lane;
 #pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) {
-      const uint32_t t = warp_hist[w][tid];
-      warp_hist[w][tid] = run;
-      run += t;
+    for (int j = 0; j < kSortItems; ++j) {
+      const int64_t idx = base + j * 32;
+      key[j] = idx < n ? ldg_stream_i32(keys_in + idx) : -1;
+      val[j] = vals_in ? (idx < n ? ldg_stream_i32(vals_in + idx) : 0) : (int)idx;
     }
-    const uint32_t excl = lookback_exclusive(status + tid, bins, tile, run);
-    digit_base[tid] = digit_start + excl;
-  }
-  __syncthreads();
+    // warp-level ranking: lanes with the same digit find each other with match.any
 #pragma unroll
-  for (int j = 0; j < kSortItems; ++j) {
-    if (key[j] >= 0) {
-      const int d = (key[j] >> shift) & (bins - 1);
-      const uint32_t pos = digit_base[d] + warp_hist[warp][d] + rank[j];
-      keys_out[pos] = key[j];
-      vals_out[pos] = val[j];
+    for (int j = 0; j < kSortItems; ++j) {
+      const bool valid = key[j] >= 0;
+      const int d = valid ? ((key[j] >> shift) & (bins - 1)) : bins;
+      const unsigned peers = __match_any_sync(kFullMask, d);
+      const int leader = __ffs(peers) - 1;
+      uint32_t b = 0;
+      if (valid && lane == leader) {
+        b = warp_hist[warp][d];
+        warp_hist[warp][d] = b + __popc(peers);
+      }
+      b = __shfl_sync(kFullMask, b, leader);
+      rank[j] = b + __popc(peers & ((1u << lane) - 1u));
+      __syncwarp();
+    }
+    __syncthreads();
+    // exclusive scan over the warps of this round
+    for (int d = tid; d < bins; d += kSortThreads) {
+      uint32_t run = 0;
+#pragma unroll
+      for (int w = 0; w < kSortWarps; ++w) {
+        const uint32_t t = warp_hist[w][d];
+        warp_hist[w][d] = run;
+        run += t;
+      }
+      round_total[d] = run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+      if (key[j] >= 0) {
+        const int d = (key[j] >> shift) & (bins - 1);
+        const uint32_t pos = digit_base[d] + warp_hist[warp][d] + rank[j];
+        keys_out[pos] = key[j];
+        vals_out[pos] = val[j];
+        if (next_hist)
+          atomicAdd(next_hist + (int64_t)(pos / (uint32_t)tile_keys) * (1 << next_bits) +
+                        ((key[j] >> next_shift) & next_mask), 1u);
+      }
+    }
+    if (r + 1 < rounds) {   // the next round continues behind this round's keys
+      __syncthreads();
+      for (int d = tid; d < bins; d += kSortThreads) digit_base[d] += round_total[d];
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------ segmentation
-// keys are sorted; a head is a position whose key differs from its predecessor. Heads are found per
-// thread (4 consecutive keys, one 128-bit load), counted with a CTA scan, and given global slots by
-// decoupled look-back. MODE 0 (prepare): also derives ranks_feat from ranks_depth.
-// MODE 1 (regroup): vals are positions into the original arrays; gathers the three rank arrays.
-template <int MODE>
-__global__ void __launch_bounds__(kHeadThreads)
-segment_heads_kernel(const int* __restrict__ keys, const int* __restrict__ vals, const int* __restrict__ n_dev,
-                     int64_t n_host, int* __restrict__ starts, int* __restrict__ n_heads_out,
-                     uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
-                     // MODE 0
-                     int* __restrict__ ranks_feat, int dhw, int hw,
-                     // MODE 1
-                     const int* __restrict__ src_rd, const int* __restrict__ src_rb, int* __restrict__ dst_rd,
-                     int* __restrict__ dst_rb) {
-  __shared__ uint32_t scan_tmp[8];
-  __shared__ int s_tile;
-  __shared__ uint32_t s_prefix;
-  const int tid = threadIdx.x;
-  if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
-  __syncthreads();
-  const int tile = s_tile;
-  const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
-  const int64_t tile_base = (int64_t)tile * kHeadTile;
-  if (tile_base >= n) return;
-  const int64_t i0 = tile_base + (int64_t)tid * kHeadItems;
-  int k[kHeadItems], v[kHeadItems];
-  const bool vec_ok = ((((uintptr_t)keys) | ((uintptr_t)vals)) & 15) == 0;   // caller buffers may be unaligned views
+// keys are sorted; a head is a position whose key differs from its predecessor.
+//   head_count_kernel : heads per tile; MODE 0 also derives ranks_feat from ranks_depth, MODE 1 gathers
+//                       the regrouped rank arrays through the argsort permutation
+//   head_scan_kernel  : exclusive scan of the tile counts (one CTA), total -> *n_heads_out
+//   head_write_kernel : interval_starts
+__device__ __forceinline__ void load_heads(const int* __restrict__ keys, int64_t i0, int64_t n, int k[kHeadItems],
+                                           bool head[kHeadItems], uint32_t& cnt) {
+  const bool vec_ok = (((uintptr_t)keys) & 15) == 0;   // caller buffers may be unaligned views
   if (vec_ok && i0 + kHeadItems <= n) {
     const int4 kk = *reinterpret_cast<const int4*>(keys + i0);
-    const int4 vv = *reinterpret_cast<const int4*>(vals + i0);
     k[0] = kk.x; k[1] = kk.y; k[2] = kk.z; k[3] = kk.w;
-    v[0] = vv.x; v[1] = vv.y; v[2] = vv.z; v[3] = vv.w;
   } else {
 #pragma unroll
-    for (int j = 0; j < kHeadItems; ++j) {
-      k[j] = (i0 + j < n) ? keys[i0 + j] : -1;
-      v[j] = (i0 + j < n) ? vals[i0 + j] : 0;
-    }
+    for (int j = 0; j < kHeadItems; ++j) k[j] = (i0 + j < n) ? keys[i0 + j] : -1;
   }
   const int prev = (i0 > 0 && i0 < n) ? keys[i0 - 1] : -1;
-  bool head[kHeadItems];
-  uint32_t cnt = 0;
+  cnt = 0;
 #pragma unroll
   for (int j = 0; j < kHeadItems; ++j) {
     head[j] = (i0 + j < n) && (k[j] != (j == 0 ? prev : k[j - 1]) || (i0 + j == 0));
     cnt += head[j];
   }
-  uint32_t total;
-  uint32_t local = block_exclusive_scan_256(cnt, scan_tmp, &total);
-  if (tid == 0) {
-    s_prefix = lookback_exclusive(status, 1, tile, total);
-    if (tile_base + kHeadTile >= n) *n_heads_out = (int)(s_prefix + total);  // last tile publishes the count
-  }
-  __syncthreads();
-  uint32_t slot = s_prefix + local;
-#pragma unroll
-  for (int j = 0; j < kHeadItems; ++j)
-    if (head[j]) starts[slot++] = (int)(i0 + j);
+}
 
-  if (MODE == 0) {
-    int f[kHeadItems];
-#pragma unroll
-    for (int j = 0; j < kHeadItems; ++j) f[j] = (v[j] / dhw) * hw + v[j] % hw;
-    if ((((uintptr_t)ranks_feat) & 15) == 0 && i0 + kHeadItems <= n) {
-      *reinterpret_cast<int4*>(ranks_feat + i0) = make_int4(f[0], f[1], f[2], f[3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < kHeadItems; ++j)
-        if (i0 + j < n) ranks_feat[i0 + j] = f[j];
-    }
-  } else {
+template <int MODE>
+__global__ void __launch_bounds__(kHeadThreads)
+head_count_kernel(const int* __restrict__ keys, const int* __restrict__ vals, const int* __restrict__ n_dev,
+                  int64_t n_host, int rounds, uint32_t* __restrict__ tile_counts,
+                  int* __restrict__ ranks_feat, int dhw, int hw,                                   // MODE 0
+                  const int* __restrict__ src_rd, const int* __restrict__ src_rb, int* __restrict__ dst_rd,
+                  int* __restrict__ dst_rb) {                                                      // MODE 1
+  __shared__ uint32_t s_cnt;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
+  const int64_t tile_base = (int64_t)blockIdx.x * rounds * kHeadRound;
+  uint32_t mine = 0;
+  for (int r = 0; r < rounds; ++r) {
+    const int64_t i0 = tile_base + (int64_t)r * kHeadRound + (int64_t)tid * kHeadItems;
+    if (i0 >= n) break;
+    int k[kHeadItems];
+    bool head[kHeadItems];
+    uint32_t cnt;
+    load_heads(keys, i0, n, k, head, cnt);
+    mine += cnt;
 #pragma unroll
     for (int j = 0; j < kHeadItems; ++j)
       if (i0 + j < n) {
-        dst_rd[i0 + j] = __ldg(src_rd + v[j]);
-        dst_rb[i0 + j] = __ldg(src_rb + v[j]);
+        const int v = vals[i0 + j];
+        if (MODE == 0) {
+          if (ranks_feat) ranks_feat[i0 + j] = (v / dhw) * hw + v % hw;
+        } else {
+          dst_rd[i0 + j] = __ldg(src_rd + v);
+          dst_rb[i0 + j] = __ldg(src_rb + v);
+        }
       }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(kFullMask, mine, o);
+  if ((tid & 31) == 0 && mine) atomicAdd(&s_cnt, mine);
+  __syncthreads();
+  if (tid == 0) tile_counts[blockIdx.x] = s_cnt;
+}
+
+__global__ void __launch_bounds__(256)
+head_scan_kernel(uint32_t* __restrict__ tile_counts, int64_t n_tiles, int* __restrict__ n_heads_out) {
+  __shared__ uint32_t scan_tmp[8];
+  uint32_t carry = 0;
+  for (int64_t t0 = 0; t0 < n_tiles; t0 += 256) {
+    const int64_t t = t0 + threadIdx.x;
+    const uint32_t v = t < n_tiles ? tile_counts[t] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan_256(v, scan_tmp, &total);
+    if (t < n_tiles) tile_counts[t] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) *n_heads_out = (int)carry;
+}
+
+__global__ void __launch_bounds__(kHeadThreads)
+head_write_kernel(const int* __restrict__ keys, const int* __restrict__ n_dev, int64_t n_host, int rounds,
+                  const uint32_t* __restrict__ tile_prefix, int* __restrict__ starts) {
+  __shared__ uint32_t scan_tmp[8];
+  const int tid = threadIdx.x;
+  const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
+  const int64_t tile_base = (int64_t)blockIdx.x * rounds * kHeadRound;
+  if (tile_base >= n) return;
+  uint32_t slot0 = tile_prefix[blockIdx.x];
+  for (int r = 0; r < rounds; ++r) {
+    const int64_t round_base = tile_base + (int64_t)r * kHeadRound;
+    if (round_base >= n) break;   // CTA-uniform
+    const int64_t i0 = round_base + (int64_t)tid * kHeadItems;
+    int k[kHeadItems];
+    bool head[kHeadItems];
+    uint32_t cnt;
+    load_heads(keys, i0, n, k, head, cnt);
+    uint32_t total;
+    uint32_t slot = slot0 + block_exclusive_scan_256(cnt, scan_tmp, &total);
+#pragma unroll
+    for (int j = 0; j < kHeadItems; ++j)
+      if (head[j]) starts[slot++] = (int)(i0 + j);
+    slot0 += total;
   }
 }
 
@@ -376,31 +478,36 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 struct SortWorkspace {
   // zeroed region
-  uint32_t* hist;        // [kMaxPasses][256]
-  uint32_t* tickets;     // [kMaxPasses + 1]
-  uint32_t* status;      // [n_passes][tiles][256] then [head tiles]
+  uint32_t* totals;      // [kMaxPasses][kMaxBins]
+  uint32_t* hist_odd;    // tile histograms built by REDs (passes 1, 3) : [n_tiles][bins]
+  uint32_t* hist_even2;  // tile histograms built by REDs (pass 2)
   size_t zero_bytes;
-  // scratch
+  // scratch (not zeroed)
+  uint32_t* hist0;       // pass-0 tile histograms, written in full by the rank / key_hist kernel
+  uint32_t* head_counts; // [head_tiles]
   int* alt_keys;
   int* alt_vals;
   size_t total_bytes;
-  int64_t sort_tiles, head_tiles;
 };
 
-static SortWorkspace carve(void* ws, int64_t n_max, int n_passes) {
+static SortWorkspace carve(void* ws, int64_t n_max, const SortPlan& plan) {
   SortWorkspace w;
-  w.sort_tiles = (n_max + kSortTile - 1) / kSortTile;
-  w.head_tiles = (n_max + kHeadTile - 1) / kHeadTile;
   char* p = (char*)ws;
   size_t off = 0;
-  w.hist = (uint32_t*)(p + off);
-  off += sizeof(uint32_t) * kMaxPasses * kRadixBins;
-  w.tickets = (uint32_t*)(p + off);
-  off += sizeof(uint32_t) * 8;
-  w.status = (uint32_t*)(p + off);
-  off += sizeof(uint32_t) * ((size_t)n_passes * w.sort_tiles * kRadixBins + w.head_tiles);
+  const size_t hist_bytes = align_up(sizeof(uint32_t) * (size_t)plan.n_tiles * kMaxBins, 256);
+  w.totals = (uint32_t*)(p + off);
+  off += sizeof(uint32_t) * kMaxPasses * kMaxBins;
+  w.hist_odd = (uint32_t*)(p + off);
+  off += plan.n_passes > 1 ? hist_bytes : 0;
+  w.hist_even2 = (uint32_t*)(p + off);
+  off += plan.n_passes > 2 ? hist_bytes : 0;
+  // a 4th pass re-uses hist_odd after the host re-zeroes it (see run_passes)
   off = align_up(off, 256);
   w.zero_bytes = off;
+  w.hist0 = (uint32_t*)(p + off);
+  off += hist_bytes;
+  w.head_counts = (uint32_t*)(p + off);
+  off += align_up(sizeof(uint32_t) * (size_t)plan.head_tiles, 256);
   w.alt_keys = (int*)(p + off);
   off += align_up(sizeof(int) * (size_t)n_max, 256);
   w.alt_vals = (int*)(p + off);
@@ -416,17 +523,34 @@ static void run_passes(const SortPlan& plan, const SortWorkspace& w, const int* 
                        const int* n_dev, int* out_keys, int* out_vals, cudaStream_t st) {
   const int* src_k = keys0;
   const int* src_v = vals0;
+  uint32_t* hist = w.hist0;
   for (int p = 0; p < plan.n_passes; ++p) {
     const bool to_out = ((plan.n_passes - 1 - p) % 2) == 0;
     int* dst_k = to_out ? out_keys : w.alt_keys;
     int* dst_v = to_out ? out_vals : w.alt_vals;
-    radix_scatter_kernel<<<(unsigned)w.sort_tiles, kSortThreads, 0, st>>>(
-        src_k, src_v, dst_k, dst_v, w.hist + p * kRadixBins, w.status + (size_t)p * w.sort_tiles * kRadixBins,
-        w.tickets + p, p == 0 ? nullptr : n_dev, n0, plan.shift[p], plan.bits[p]);
+    const int bins = 1 << plan.bits[p];
+    uint32_t* next = nullptr;
+    if (p + 1 < plan.n_passes) {
+      next = (p + 1 == 2) ? w.hist_even2 : w.hist_odd;
+      if (p + 1 == 3) cudaMemsetAsync(w.hist_odd, 0, sizeof(uint32_t) * (size_t)plan.n_tiles * kMaxBins, st);
+    }
+    tile_scan_kernel<<<bins, 256, 0, st>>>(hist, plan.n_tiles, bins);
+    count_launch();
+    radix_scatter_kernel<<<(unsigned)plan.n_tiles, kSortThreads, 0, st>>>(
+        src_k, src_v, dst_k, dst_v, w.totals + p * kMaxBins, hist, next, p == 0 ? nullptr : n_dev, n0, plan.shift[p],
+        plan.bits[p], plan.rounds, next ? plan.shift[p + 1] : 0, next ? plan.bits[p + 1] : 1);
     count_launch();
     src_k = dst_k;
     src_v = dst_v;
+    hist = next;
   }
+}
+
+static void magic_div(int d, uint32_t* mul, int* shift) {
+  int s = 0;
+  while (((int64_t)1 << s) < d) ++s;
+  *shift = 31 + s;
+  *mul = (uint32_t)((((uint64_t)1 << (31 + s)) / (uint64_t)d) + 1);
 }
 
 }  // namespace bevpool
@@ -453,8 +577,8 @@ static int check_grid(const bevpool_grid_t* g, int64_t* p0, int64_t* total_voxel
   if (g->nx[0] <= 0 || g->nx[1] <= 0 || g->nx[2] <= 0) return BEVPOOL_ERR_BAD_ARG;
   const int64_t n = (int64_t)g->b * g->n * g->d * g->h * g->w;
   const int64_t v = (int64_t)g->b * g->nx[0] * g->nx[1] * g->nx[2];
-  if (n >= ((int64_t)1 << 30) || v >= ((int64_t)1 << 31) - 1) return BEVPOOL_ERR_OVERFLOW;  // int32 ranks, 30-bit look-back counters
-  if ((int64_t)g->b * g->n > 65535) return BEVPOOL_ERR_BAD_ARG;
+  if (n >= ((int64_t)1 << 30) || v >= ((int64_t)1 << 31) - 1) return BEVPOOL_ERR_OVERFLOW;  // int32 ranks
+  if ((int64_t)g->b * g->n > 4096) return BEVPOOL_ERR_BAD_ARG;   // camera table lives in shared memory
   *p0 = n;
   *total_voxels = v;
   return BEVPOOL_OK;
@@ -464,9 +588,9 @@ extern "C" size_t bevpool_prepare_v2_workspace_bytes(const bevpool_grid_t* g) {
   int64_t p0, v;
   if (check_grid(g, &p0, &v) != BEVPOOL_OK) return 0;
   if (p0 == 0) return 256;
-  const SortPlan plan = make_plan(v > 0 ? v - 1 : 0);
+  const SortPlan plan = make_plan(v > 0 ? v - 1 : 0, p0);
   // + a private point_rank array in case the caller does not want one
-  return carve(nullptr, p0, plan.n_passes).total_bytes + align_up(sizeof(int) * (size_t)p0, 256);
+  return carve(nullptr, p0, plan).total_bytes + align_up(sizeof(int) * (size_t)p0, 256);
 }
 
 extern "C" int bevpool_prepare_v2(const float* coor, const float* frustum, const float* rots, const float* trans,
@@ -481,19 +605,22 @@ extern "C" int bevpool_prepare_v2(const float* coor, const float* frustum, const
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int32_t), st);
   if (p0 == 0) return launch_status();
-  if (!ranks_bev || !ranks_depth || !ranks_feat || !interval_starts || !interval_lengths || !workspace)
-    return BEVPOOL_ERR_BAD_ARG;
+  if (!ranks_bev || !ranks_depth || !workspace) return BEVPOOL_ERR_BAD_ARG;
+  if ((interval_starts == nullptr) != (interval_lengths == nullptr)) return BEVPOOL_ERR_BAD_ARG;
   if (!coor && (!frustum || !rots || !trans)) return BEVPOOL_ERR_BAD_ARG;
   if (workspace_bytes < bevpool_prepare_v2_workspace_bytes(g)) return BEVPOOL_ERR_WORKSPACE;
 
-  const SortPlan plan = make_plan(v - 1);
-  const SortWorkspace w = carve(workspace, p0, plan.n_passes);
+  const SortPlan plan = make_plan(v - 1, p0);
+  const SortWorkspace w = carve(workspace, p0, plan);
   if (!point_rank) point_rank = (int*)((char*)workspace + w.total_bytes);
   cudaMemsetAsync(workspace, 0, w.zero_bytes, st);
 
   GridDev gd;
-  gd.dhw = (int64_t)g->d * g->h * g->w;
+  gd.n_points = p0;
+  gd.dhw = g->d * g->h * g->w;
+  magic_div(gd.dhw, &gd.dhw_mul, &gd.dhw_shift);
   gd.n_cams = g->n;
+  gd.bn = g->b * g->n;
   gd.nx = g->nx[0];
   gd.ny = g->nx[1];
   gd.nz = g->nx[2];
@@ -501,36 +628,46 @@ extern "C" int bevpool_prepare_v2(const float* coor, const float* frustum, const
     gd.lo[a] = g->lo[a];
     gd.dx[a] = g->dx[a];
   }
-  const int bn = g->b * g->n;
-  // ~2 CTAs per SM overall; each CTA stays inside one camera
-  int bx = (int)((gd.dhw + 255) / 256);
-  const int want = (kNumSMs * 8 + bn - 1) / bn;
-  if (bx > want) bx = want;
-  if (bx < 1) bx = 1;
-  if (coor)
-    point_rank_kernel<true><<<dim3(bx, bn), 256, 0, st>>>(coor, frustum, rots, trans, gd, plan, point_rank, w.hist, counts_dev);
-  else
-    point_rank_kernel<false><<<dim3(bx, bn), 256, 0, st>>>(coor, frustum, rots, trans, gd, plan, point_rank, w.hist, counts_dev);
+  if (coor) {
+    point_rank_kernel<true><<<(unsigned)plan.n_tiles, kSortThreads, 0, st>>>(coor, frustum, rots, trans, gd, plan,
+                                                                            point_rank, w.hist0, w.totals, counts_dev);
+  } else {
+    const size_t cam_smem = sizeof(float) * 12 * (size_t)gd.bn;
+    static size_t attr = 0;
+    if (cam_smem + 9 * 1024 > 48 * 1024 && cam_smem > attr) {
+      cudaFuncSetAttribute(point_rank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cam_smem);
+      attr = cam_smem;
+    }
+    point_rank_kernel<false><<<(unsigned)plan.n_tiles, kSortThreads, cam_smem, st>>>(
+        coor, frustum, rots, trans, gd, plan, point_rank, w.hist0, w.totals, counts_dev);
+  }
   count_launch();
 
   run_passes(plan, w, point_rank, nullptr, p0, counts_dev, ranks_bev, ranks_depth, st);
 
-  segment_heads_kernel<0><<<(unsigned)w.head_tiles, kHeadThreads, 0, st>>>(
-      ranks_bev, ranks_depth, counts_dev, p0, interval_starts, counts_dev + 1,
-      w.status + (size_t)plan.n_passes * w.sort_tiles * kRadixBins, w.tickets + plan.n_passes, ranks_feat,
-      (int)gd.dhw, g->h * g->w, nullptr, nullptr, nullptr, nullptr);
-  count_launch();
-  int lb = (int)((v < p0 ? v : p0) + 255) / 256;
-  if (lb > kNumSMs * 8) lb = kNumSMs * 8;
-  if (lb < 1) lb = 1;
-  interval_lengths_kernel<<<lb, 256, 0, st>>>(interval_starts, counts_dev + 1, counts_dev, p0, interval_lengths);
-  count_launch();
+  if (interval_starts || ranks_feat) {
+    head_count_kernel<0><<<(unsigned)plan.head_tiles, kHeadThreads, 0, st>>>(
+        ranks_bev, ranks_depth, counts_dev, p0, plan.head_rounds, w.head_counts, ranks_feat, gd.dhw, g->h * g->w,
+        nullptr, nullptr, nullptr, nullptr);
+    count_launch();
+  }
+  if (interval_starts) {
+    head_scan_kernel<<<1, 256, 0, st>>>(w.head_counts, plan.head_tiles, counts_dev + 1);
+    head_write_kernel<<<(unsigned)plan.head_tiles, kHeadThreads, 0, st>>>(ranks_bev, counts_dev, p0, plan.head_rounds,
+                                                                         w.head_counts, interval_starts);
+    int lb = (int)(((v < p0 ? v : p0) + 255) / 256);
+    if (lb > kNumSMs * 8) lb = kNumSMs * 8;
+    if (lb < 1) lb = 1;
+    interval_lengths_kernel<<<lb, 256, 0, st>>>(interval_starts, counts_dev + 1, counts_dev, p0, interval_lengths);
+    count_launch(3);
+  }
   return launch_status();
 }
 
 extern "C" size_t bevpool_v2_backward_regroup_workspace_bytes(int64_t n_points) {
   if (n_points <= 0) return 256;
-  return carve(nullptr, n_points, kMaxPasses).total_bytes + align_up(sizeof(int) * (size_t)n_points, 256);
+  SortPlan plan = make_plan(((int64_t)1 << 31) - 2, n_points);   // worst-case pass count
+  return carve(nullptr, n_points, plan).total_bytes + align_up(sizeof(int) * (size_t)n_points, 256);
 }
 
 extern "C" int bevpool_v2_backward_regroup(const int32_t* ranks_depth, const int32_t* ranks_feat,
@@ -548,25 +685,27 @@ extern "C" int bevpool_v2_backward_regroup(const int32_t* ranks_depth, const int
       !interval_starts_bp || !interval_lengths_bp || !workspace)
     return BEVPOOL_ERR_BAD_ARG;
   if (workspace_bytes < bevpool_v2_backward_regroup_workspace_bytes(n_points)) return BEVPOOL_ERR_WORKSPACE;
-  const SortPlan plan = make_plan(max_ranks_feat);
-  const SortWorkspace w = carve(workspace, n_points, plan.n_passes);
-  int* order = (int*)((char*)workspace + carve(nullptr, n_points, kMaxPasses).total_bytes);
+  const SortPlan plan = make_plan(max_ranks_feat, n_points);
+  const SortWorkspace w = carve(workspace, n_points, plan);
+  // the argsort permutation lives behind the largest possible carve so it never overlaps
+  const SortPlan worst = make_plan(((int64_t)1 << 31) - 2, n_points);
+  int* order = (int*)((char*)workspace + carve(nullptr, n_points, worst).total_bytes);
   cudaMemsetAsync(workspace, 0, w.zero_bytes, st);
-  int hb = (int)((n_points + 2047) / 2048);
-  if (hb > kNumSMs * 8) hb = kNumSMs * 8;
-  key_hist_kernel<<<hb, 256, 0, st>>>(ranks_feat, n_points, plan, w.hist);
+  key_hist_kernel<<<(unsigned)plan.n_tiles, kSortThreads, 0, st>>>(ranks_feat, n_points, plan, w.hist0, w.totals);
   count_launch();
   // argsort: sorted keys land in ranks_feat_bp, original positions in `order`
   run_passes(plan, w, ranks_feat, nullptr, n_points, nullptr, ranks_feat_bp, order, st);
-  segment_heads_kernel<1><<<(unsigned)w.head_tiles, kHeadThreads, 0, st>>>(
-      ranks_feat_bp, order, nullptr, n_points, interval_starts_bp, n_intervals_bp_dev,
-      w.status + (size_t)plan.n_passes * w.sort_tiles * kRadixBins, w.tickets + plan.n_passes, nullptr, 1, 1,
-      ranks_depth, ranks_bev, ranks_depth_bp, ranks_bev_bp);
-  count_launch();
+  head_count_kernel<1><<<(unsigned)plan.head_tiles, kHeadThreads, 0, st>>>(
+      ranks_feat_bp, order, nullptr, n_points, plan.head_rounds, w.head_counts, nullptr, 1, 1, ranks_depth, ranks_bev,
+      ranks_depth_bp, ranks_bev_bp);
+  head_scan_kernel<<<1, 256, 0, st>>>(w.head_counts, plan.head_tiles, n_intervals_bp_dev);
+  head_write_kernel<<<(unsigned)plan.head_tiles, kHeadThreads, 0, st>>>(ranks_feat_bp, nullptr, n_points,
+                                                                       plan.head_rounds, w.head_counts,
+                                                                       interval_starts_bp);
   int lb = (int)((n_points + 255) / 256);
   if (lb > kNumSMs * 8) lb = kNumSMs * 8;
   interval_lengths_kernel<<<lb, 256, 0, st>>>(interval_starts_bp, n_intervals_bp_dev, nullptr, n_points,
                                               interval_lengths_bp);
-  count_launch();
+  count_launch(4);
   return launch_status();
 }

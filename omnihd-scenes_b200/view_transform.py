@@ -97,7 +97,9 @@ class _Prepared:
     __slots__ = ("rb", "rd", "rf", "starts", "lengths", "counts", "point_rank", "bn", "d", "h", "w", "hw", "p0")
 
 
-def _prepare_device(coor, frustum, rots, trans, B, N, D, H, W, dx, bx, nx, device):
+def _prepare_device(coor, frustum, rots, trans, B, N, D, H, W, dx, bx, nx, device, want_intervals=True):
+    """want_intervals=False (fused path): only the sorted (ranks_bev, ranks_depth) lists, the kept count and
+    point_rank are produced — ranks_feat is derivable and the interval arrays are replaced by the voxel table."""
     lib = _lib.load()
     g = _grid_struct(B, N, D, H, W, dx, bx, nx)
     p0 = B * N * D * H * W
@@ -106,11 +108,14 @@ def _prepare_device(coor, frustum, rots, trans, B, N, D, H, W, dx, bx, nx, devic
         raise ValueError("problem too large for int32 ranks: shard the frame batch")
     out = _Prepared()
     pad = lambda n: (max(n, 1) + 63) // 64 * 64            # rows stay 256-byte aligned (128-bit loads)
-    ranks = torch.empty((3, pad(p0)), dtype=torch.int32, device=device)[:, :max(p0, 1)]
-    n_int = max(min(p0, vtot), 1)
-    inter = torch.empty((2, pad(n_int)), dtype=torch.int32, device=device)[:, :n_int]
-    out.rb, out.rd, out.rf = ranks[0], ranks[1], ranks[2]
-    out.starts, out.lengths = inter[0], inter[1]
+    ranks = torch.empty((3 if want_intervals else 2, pad(p0)), dtype=torch.int32, device=device)[:, :max(p0, 1)]
+    out.rb, out.rd = ranks[0], ranks[1]
+    out.rf = out.starts = out.lengths = None
+    if want_intervals:
+        n_int = max(min(p0, vtot), 1)
+        inter = torch.empty((2, pad(n_int)), dtype=torch.int32, device=device)[:, :n_int]
+        out.rf = ranks[2]
+        out.starts, out.lengths = inter[0], inter[1]
     out.counts = torch.empty(2, dtype=torch.int32, device=device)
     out.point_rank = torch.empty(max(p0, 1), dtype=torch.int32, device=device)
     out.bn, out.d, out.h, out.w, out.hw, out.p0 = B * N, D, H, W, H * W, p0
@@ -261,6 +266,6 @@ class LSSViewTransform(nn.Module):
         if C % 4:
             raise ValueError("the fused path needs C % 4 == 0; use voxel_pooling_v2 for other channel counts")
         pr = _prepare_device(None, self.frustum, rots.contiguous(), trans.contiguous(), B, N, D, H, W,
-                             self.dx, self.bx, self.nx, rots.device)
+                             self.dx, self.bx, self.nx, rots.device, want_intervals=False)
         shape = (B, int(self.nx[2]), int(self.nx[1]), int(self.nx[0]), C)
         return _FusedViewPool.apply(depth, feat, pr, shape)

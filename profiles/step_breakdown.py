@@ -25,7 +25,7 @@ stages = ["prepare", "feat_transpose", "voxel_table", "pool_fwd", "og_transpose"
 
 def run(s, upto):
     st = torch.cuda.current_stream().cuda_stream
-    pr = vt._prepare_device(None, view.frustum, s["rots"], s["trans"], B, N, D, H, W, view.dx, view.bx, view.nx, dev)
+    pr = vt._prepare_device(None, view.frustum, s["rots"], s["trans"], B, N, D, H, W, view.dx, view.bx, view.nx, dev, want_intervals=False)
     if upto == 0: return pr
     fcl = s["feat"].new_empty((B * N, H, W, C)); bp._launch_transpose(s["feat"], fcl, B * N, C, H * W, True)
     if upto == 1: return fcl

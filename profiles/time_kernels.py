@@ -19,7 +19,7 @@ sets = []
 for s in range(NS):
     rots, trans = pkg.synthetic.camera_ring(B, N, cfg.final_dim, seed=s)
     depth, feat, gout = pkg.synthetic.pool_inputs(cfg, batch=B, seed=s)
-    pr = pkg.view_transform._prepare_device(None, view.frustum, rots.to(dev), trans.to(dev), B, N, D, H, W, view.dx, view.bx, view.nx, dev)
+    pr = pkg.view_transform._prepare_device(None, view.frustum, rots.to(dev), trans.to(dev), B, N, D, H, W, view.dx, view.bx, view.nx, dev, want_intervals=False)
     f = feat.to(dev, dt)
     fcl = f.new_empty((B * N, H, W, C))
     bp._launch_transpose(f, fcl, B * N, C, H * W, True)
