@@ -70,6 +70,10 @@ struct Vec4<float> {
   static __device__ __forceinline__ void store(float* base, int64_t elem, float4 v) {
     stg_stream_f4(reinterpret_cast<float4*>(base + elem), v);
   }
+  // row that a following kernel gathers from: ordinary write-back store (stays in L2)
+  static __device__ __forceinline__ void store_keep(float* base, int64_t elem, float4 v) {
+    *reinterpret_cast<float4*>(base + elem) = v;
+  }
   static __device__ __forceinline__ float load1(const float* base, int64_t elem) { return __ldg(base + elem); }
   static __device__ __forceinline__ void store1(float* base, int64_t elem, float v) { base[elem] = v; }
   static __device__ __forceinline__ void store1s(float* base, int64_t elem, float v) { stg_stream_f32(base + elem, v); }
@@ -99,6 +103,14 @@ struct Vec4<__nv_bfloat16> {
     r.x = *reinterpret_cast<uint32_t*>(&lo);
     r.y = *reinterpret_cast<uint32_t*>(&hi);
     stg_stream_u2(reinterpret_cast<uint2*>(base + elem), r);
+  }
+  static __device__ __forceinline__ void store_keep(__nv_bfloat16* base, int64_t elem, float4 v) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&lo);
+    r.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(base + elem) = r;
   }
   static __device__ __forceinline__ float load1(const __nv_bfloat16* base, int64_t elem) {
     return __bfloat162float(base[elem]);

@@ -229,6 +229,43 @@ grid_transpose_kernel(const T* __restrict__ src, T* __restrict__ dst, int rows, 
   }
 }
 
+// [B][C][S] -> [B][S][C] for C % 4 == 0, C <= 128: a CTA moves ALL channels of 64 consecutive positions, so
+// both sides are 128-bit and fully coalesced (reads: 256-byte row pieces, writes: 64*C*4 contiguous bytes).
+constexpr int kTcCols = 64;
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose_to_channels_last_kernel(const T* __restrict__ src, T* __restrict__ dst, int c, int64_t cols,
+                                  int64_t tiles_per_batch) {
+  extern __shared__ float t[];   // [c][kTcCols + 1]
+  const int64_t b = blockIdx.x / tiles_per_batch;
+  const int64_t col0 = (blockIdx.x % tiles_per_batch) * kTcCols;
+  const int ncol = (int)min((int64_t)kTcCols, cols - col0);
+  const T* s = src + (b * c) * cols + col0;
+  T* d = dst + (b * cols + col0) * c;
+  const bool vec = (ncol == kTcCols) && ((cols & 3) == 0) && ((((uintptr_t)src) & 15) == 0);
+  if (vec) {
+    for (int i = threadIdx.x; i < c * (kTcCols / 4); i += 256) {
+      const int ch = i / (kTcCols / 4), q = i % (kTcCols / 4);
+      const float4 v = Vec4<T>::load_stream(s, (int64_t)ch * cols + 4 * q);
+      float* o = t + ch * (kTcCols + 1) + 4 * q;
+      o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < c * kTcCols; i += 256) {
+      const int ch = i / kTcCols, q = i % kTcCols;
+      if (q < ncol) t[ch * (kTcCols + 1) + q] = Vec4<T>::load1(s, (int64_t)ch * cols + q);
+    }
+  }
+  __syncthreads();
+  const int c4 = c >> 2;
+  for (int i = threadIdx.x; i < ncol * c4; i += 256) {
+    const int col = i / c4, q = i % c4;
+    const float* p = t + (4 * q) * (kTcCols + 1) + col;
+    Vec4<T>::store_keep(d, (int64_t)col * c + 4 * q,
+                        make_float4(p[0], p[kTcCols + 1], p[2 * (kTcCols + 1)], p[3 * (kTcCols + 1)]));
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static inline int grid_for_warps(int64_t n_items, int warps_per_block, int max_blocks) {
   int64_t b = (n_items + warps_per_block - 1) / warps_per_block;
@@ -266,6 +303,18 @@ static int backward_t(const void* og, void* dg, void* fg, const void* depth, con
   else
     pool_bwd_scalar_kernel<T><<<grid, kPoolThreads, 0, st>>>((const T*)og, (const T*)depth, (const T*)feat, rd, rf,
                                                              rb, starts, lengths, n_intervals, c, (T*)dg, (T*)fg);
+  count_launch();
+  return launch_status();
+}
+
+template <typename T>
+static int transpose_cl_t(const void* src, void* dst, int b, int c, int64_t cols, cudaStream_t st) {
+  const int64_t tiles_per_batch = (cols + kTcCols - 1) / kTcCols;
+  const int64_t total = (int64_t)b * tiles_per_batch;
+  if (total == 0) return 0;
+  if (total > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
+  const size_t smem = sizeof(float) * (size_t)c * (kTcCols + 1);
+  transpose_to_channels_last_kernel<T><<<(unsigned)total, 256, smem, st>>>((const T*)src, (T*)dst, c, cols, tiles_per_batch);
   count_launch();
   return launch_status();
 }
@@ -332,12 +381,15 @@ extern "C" int bevpool_grid_transpose(const void* src, void* dst, int b, int c, 
   if (!src || !dst) return BEVPOOL_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   // BCZYX is [B][c][zyx]; BZYXC is [B][zyx][c]
+  const bool fast = to_channels_last && c % 4 == 0 && c <= 128 && (((uintptr_t)dst) & 15) == 0;
   if (dtype == BEVPOOL_F32) {
+    if (fast) return transpose_cl_t<float>(src, dst, b, c, zyx, st);
     if (to_channels_last) return transpose_t<float>(src, dst, b, c, zyx, st);
     if (zyx > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
     return transpose_t<float>(src, dst, b, (int)zyx, c, st);
   }
   if (dtype == BEVPOOL_BF16) {
+    if (fast && (zyx & 3) == 0) return transpose_cl_t<__nv_bfloat16>(src, dst, b, c, zyx, st);
     if (to_channels_last) return transpose_t<__nv_bfloat16>(src, dst, b, c, zyx, st);
     if (zyx > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
     return transpose_t<__nv_bfloat16>(src, dst, b, (int)zyx, c, st);

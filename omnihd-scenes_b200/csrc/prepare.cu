@@ -210,7 +210,7 @@ point_rank_kernel(const float* __restrict__ coor, const float* __restrict__ frus
   if (lane == 0 && kept) atomicAdd(&s_kept, kept);
   __syncthreads();
   const int bins0 = 1 << plan.bits[0];
-  for (int d = tid; d < bins0; d += kSortThreads) tile_hist0[(int64_t)blockIdx.x * bins0 + d] = sh[0][d];
+  for (int d = tid; d < bins0; d += kSortThreads) tile_hist0[(int64_t)d * gridDim.x + blockIdx.x] = sh[0][d];
   for (int i = tid; i < plan.n_passes * kMaxBins; i += kSortThreads) {
     const uint32_t v = (&sh[0][0])[i];
     if (v) atomicAdd(totals + i, v);
@@ -237,7 +237,7 @@ key_hist_kernel(const int* __restrict__ keys, int64_t n, SortPlan plan, uint32_t
   }
   __syncthreads();
   const int bins0 = 1 << plan.bits[0];
-  for (int d = tid; d < bins0; d += kSortThreads) tile_hist0[(int64_t)blockIdx.x * bins0 + d] = sh[0][d];
+  for (int d = tid; d < bins0; d += kSortThreads) tile_hist0[(int64_t)d * gridDim.x + blockIdx.x] = sh[0][d];
   for (int i = tid; i < plan.n_passes * kMaxBins; i += kSortThreads) {
     const uint32_t v = (&sh[0][0])[i];
     if (v) atomicAdd(totals + i, v);
@@ -245,7 +245,8 @@ key_hist_kernel(const int* __restrict__ keys, int64_t n, SortPlan plan, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------ tile scan
-// hist is [n_tiles][bins]; CTA d turns column d into its exclusive prefix along tiles (in place).
+// hist is digit-major [bins][n_tiles]; CTA d turns row d into its exclusive prefix along tiles (in place,
+// coalesced).
 __global__ void __launch_bounds__(256)
 tile_scan_kernel(uint32_t* __restrict__ hist, int64_t n_tiles, int bins) {
   __shared__ uint32_t scan_tmp[8];
@@ -253,17 +254,17 @@ tile_scan_kernel(uint32_t* __restrict__ hist, int64_t n_tiles, int bins) {
   uint32_t carry = 0;
   for (int64_t t0 = 0; t0 < n_tiles; t0 += 256) {
     const int64_t t = t0 + threadIdx.x;
-    const uint32_t v = t < n_tiles ? hist[t * bins + d] : 0u;
+    const uint32_t v = t < n_tiles ? hist[(int64_t)d * n_tiles + t] : 0u;
     uint32_t total;
     const uint32_t ex = block_exclusive_scan_256(v, scan_tmp, &total);
-    if (t < n_tiles) hist[t * bins + d] = carry + ex;
+    if (t < n_tiles) hist[(int64_t)d * n_tiles + t] = carry + ex;
     carry += total;
   }
 }
 
 // ------------------------------------------------------------------------------------------ radix pass
 // One stable LSD pass. Keys < 0 are dropped (pass 0 = compaction). vals_in == nullptr means
-// "value = position" (first pass of an argsort). tile_prefix[tile][bins] holds, per digit, the number
+// "value = position" (first pass of an argsort). tile_prefix[digit][tile] holds, per digit, the number
 // of keys with that digit in earlier tiles. next_hist (optional): tile histograms of the NEXT pass,
 // accumulated at the destination positions.
 __global__ void __launch_bounds__(kSortThreads)
@@ -290,7 +291,7 @@ radix_scatter_kernel(const int* __restrict__ keys_in, const int* __restrict__ va
       const int d = d0 + tid;
       uint32_t total;
       const uint32_t ex = block_exclusive_scan_256(d < bins ? __ldg(digit_totals + d) : 0u, scan_tmp, &total);
-      if (d < bins) digit_base[d] = carry + ex + __ldg(tile_prefix + (int64_t)blockIdx.x * bins + d);
+      if (d < bins) digit_base[d] = carry + ex + __ldg(tile_prefix + (int64_t)d * gridDim.x + blockIdx.x);
       carry += total;
     }
   }
@@ -347,8 +348,7 @@ radix_scatter_kernel(const int* __restrict__ keys_in, const int* __restrict__ va
         keys_out[pos] = key[j];
         vals_out[pos] = val[j];
         if (next_hist)
-          atomicAdd(next_hist + (int64_t)(pos / (uint32_t)tile_keys) * (1 << next_bits) +
-                        ((key[j] >> next_shift) & next_mask), 1u);
+          atomicAdd(next_hist + (int64_t)((key[j] >> next_shift) & next_mask) * gridDim.x + pos / (uint32_t)tile_keys, 1u);
       }
     }
     if (r + 1 < rounds) {   // the next round continues behind this round's keys
