@@ -342,8 +342,14 @@ def run_native_arm(args):
     dom = "pool_bwd_dense" if kernels["pool_bwd_dense"] >= kernels["pool_fwd_dense"] else "pool_fwd_dense"
     dom_bytes = ab["bwd"] if dom == "pool_bwd_dense" else ab["fwd"]
     achieved = dom_bytes / kernels[dom] / 1e9
+    traffic = None
+    try:     # dram bytes per launch from the committed `ncu --set full` capture (cannot be measured live)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom) \
+            if args.config == WORKLOAD and B == cfg.batch else None
+    except OSError:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "frac_of_8TBps_nominal": achieved / 8000.0, "traffic": None,
+                "frac": achieved / peak, "frac_of_8TBps_nominal": achieved / 8000.0, "traffic": traffic,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "us_per_launch": kernels[dom] * 1e6,
                 "all_kernels": {
