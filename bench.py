@@ -315,7 +315,7 @@ def run_native_arm(args):
             p = prs[k]
             lib.bevpool_v2_backward_dense(og_cl[k].data_ptr(), dgs[k].data_ptr(), fgs[k].data_ptr(),
                                           sets[k]["depth"].data_ptr(), feat_cl[k].data_ptr(), p.point_rank.data_ptr(),
-                                          p.bn, p.d, p.h, p.w, C, 1, code, st)
+                                          p.bn, p.d, p.h, p.w, C, 1, 1 if Z == 1 else 0, code, st)
 
         def k_prep(i):
             k = i % N_BUFFER_SETS

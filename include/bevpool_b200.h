@@ -144,10 +144,14 @@ int bevpool_v2_forward_dense(const void* depth, const void* feat, void* out,
  * bins of every feature pixel through point_rank, writes EVERY element of depth_grad
  * ([BN,D,H,W], zeros for dropped points) and feat_grad — no memset, no argsort.
  * out_grad is [B,Z,Y,X,C] (use bevpool_grid_transpose for a [B,C,Z,Y,X] gradient).
- * feat is [BN,H,W,C]; feat_grad is [BN,H,W,C] (feat_grad_nchw == 0) or [BN,C,H,W] (!= 0). */
+ * feat is [BN,H,W,C]; feat_grad is [BN,H,W,C] (feat_grad_nchw == 0) or [BN,C,H,W] (!= 0).
+ * column_hint != 0 selects the kernel that walks the 4 pixels of an image column jointly and loads an
+ * out_grad row once for all of them that share the voxel — the common case on Z == 1 BEV grids; results
+ * are the same either way, only the speed differs (pass nx[2] == 1). */
 int bevpool_v2_backward_dense(const void* out_grad, void* depth_grad, void* feat_grad,
                               const void* depth, const void* feat, const int32_t* point_rank,
-                              int bn, int d, int h, int w, int c, int feat_grad_nchw, int dtype, void* stream);
+                              int bn, int d, int h, int w, int c, int feat_grad_nchw, int column_hint,
+                              int dtype, void* stream);
 
 /* [B,C,Z,Y,X] <-> [B,Z,Y,X,C] tile transpose (bev_pool.py:69 / :91 as one coalesced pass).
  * to_channels_last != 0: src is BCZYX, dst is BZYXC; else the reverse. */

@@ -182,13 +182,13 @@ def _backward_general(out_grad_cl, depth, feat, rd, rf, rb):
     return depth_grad, feat_grad
 
 
-def _backward_dense(out_grad_cl, depth, feat, plan):
+def _backward_dense(out_grad_cl, depth, feat, plan, column_hint):
     lib = _lib.load()
     depth_grad = torch.empty_like(depth)
     feat_grad = torch.empty_like(feat)
     _lib.check(lib.bevpool_v2_backward_dense(_ptr(out_grad_cl), _ptr(depth_grad), _ptr(feat_grad), _ptr(depth),
                                              _ptr(feat), _ptr(plan.point_rank), plan.bn, plan.d, plan.h, plan.w,
-                                             feat.shape[-1], 0, _dtype_code(feat), _stream()),
+                                             feat.shape[-1], 0, 1 if column_hint else 0, _dtype_code(feat), _stream()),
                "bevpool_v2_backward_dense")
     return depth_grad, feat_grad
 
@@ -256,7 +256,7 @@ class _BevPoolV2Fused(torch.autograd.Function):
         og_cl = out_grad.new_empty((B, Z, Y, X, C))
         _launch_transpose(out_grad, og_cl, B, C, Z * Y * X, to_channels_last=True)
         if ctx.plan is not None and C % 4 == 0:
-            depth_grad, feat_grad = _backward_dense(og_cl, depth, feat, ctx.plan)
+            depth_grad, feat_grad = _backward_dense(og_cl, depth, feat, ctx.plan, column_hint=(Z == 1))
         else:
             depth_grad, feat_grad = _backward_general(og_cl, depth, feat, rd, rf, rb)
         return depth_grad.to(ctx.in_dtypes[0]), feat_grad.to(ctx.in_dtypes[1]), None, None, None, None, None, None

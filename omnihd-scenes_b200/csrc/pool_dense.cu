@@ -520,6 +520,219 @@ pool_bwd_block_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
   }
 }
 
+// ------------------------------------------------------------------------------------------ backward, joint columns
+// Same contract as pool_bwd_block_kernel, for grids where the pixels of one image column mostly land in the
+// same voxel at a given depth bin (Z == 1 BEV grids: the 4 pixels (h0..h0+3, w) of a warp's column differ only
+// in height). The warp walks its 4 pixels JOINTLY: per depth bin the distinct voxel ranks among the 4 pixels
+// become list entries {rank, bin, pixel mask}; one out_grad row is loaded per entry and applied to every pixel
+// in the mask (4 dot products + 4 feat_grad updates per row instead of one load per point). Grids where the
+// ranks differ simply get more entries with single-bit masks — the result is identical either way.
+constexpr int kJointPad = kPixBlock + 1;   // row stride of the staged [d][pixel] arrays (conflict-free by bin)
+constexpr int kJointList = 128;            // list entries per 32-bin round: 4 pixels x 32 bins
+
+template <typename T>
+__global__ void __launch_bounds__(kBwdThreads, 3)
+pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, const T* __restrict__ feat,
+                      const int* __restrict__ point_rank, BwdParams prm, T* __restrict__ depth_grad,
+                      T* __restrict__ feat_grad) {
+  extern __shared__ unsigned char smem_raw[];
+  int* s_rank = reinterpret_cast<int*>(smem_raw);                                   // [d][33]
+  float* s_depth = reinterpret_cast<float*>(smem_raw) + (size_t)prm.d * kJointPad;   // [d][33]
+  float* s_dg = s_depth + (size_t)prm.d * kJointPad;                                 // [d][33]
+  int2* s_list = reinterpret_cast<int2*>(                                            // [8 warps][128] {rank, bin | mask << 16}
+      (reinterpret_cast<uintptr_t>(s_dg + (size_t)prm.d * kJointPad) + 7) & ~(uintptr_t)7);
+  float* s_fg = reinterpret_cast<float*>(s_list + (size_t)kBwdWarps * kJointList);   // [cw][33] (NCHW output only)
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int c4 = prm.c >> 2;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const int blk = blockIdx.x;
+  const int per_img = prm.blocks_w * prm.blocks_h;
+  const int bn = blk / per_img;
+  const int brem = blk - bn * per_img;
+  const int bh = brem / prm.blocks_w, bw = brem - bh * prm.blocks_w;
+  const int h0 = bh * kPixH, w0 = bw * kPixW;
+  const int64_t hw = (int64_t)prm.h * prm.w;
+  const int64_t img_base = (int64_t)bn * prm.d * hw;
+
+  // ---- stage point_rank / depth of the block: 8 consecutive w = one 32-byte sector per (d, h)
+  {
+    const int px = threadIdx.x & 31;
+    const int hh = h0 + (px >> 3), ww = w0 + (px & 7);
+    const bool in = hh < prm.h && ww < prm.w;
+    const int64_t o0 = img_base + (int64_t)hh * prm.w + ww;
+    for (int dd = threadIdx.x >> 5; dd < prm.d; dd += kBwdWarps) {
+      int r = -1;
+      float dv = 0.f;
+      if (in) {
+        r = ldg_stream_i32(point_rank + o0 + dd * hw);
+        dv = Vec4<T>::load1(depth, o0 + dd * hw);   // unconditional: no load-to-load dependency
+      }
+      s_rank[dd * kJointPad + px] = r;
+      s_depth[dd * kJointPad + px] = dv;
+      s_dg[dd * kJointPad + px] = 0.f;
+    }
+  }
+  __syncthreads();
+
+  int2* my_list = s_list + (size_t)warp * kJointList;
+  const int ww = w0 + warp;   // this warp's image column; its pixels are px = hl*8 + warp, hl = 0..3
+  for (int cb = 0; cb < c4; cb += 32) {
+    const bool act = cb + lane < c4;
+    const int cw = min(prm.c - 4 * cb, 128);
+    const int lane_c = 4 * (cb + min(lane, c4 - 1 - cb));
+    const T* og_lane = og + lane_c;
+    float4 fv[kPixH], fg[kPixH];
+#pragma unroll
+    for (int p = 0; p < kPixH; ++p) {
+      fg[p] = zero;
+      const int hh = h0 + p;
+      fv[p] = (ww < prm.w && hh < prm.h)
+                  ? Vec4<T>::load(feat, ((int64_t)bn * hw + (int64_t)hh * prm.w + ww) * prm.c + lane_c) : zero;
+    }
+    if (ww < prm.w) {   // warp-uniform
+      for (int d0 = 0; d0 < prm.d; d0 += 32) {
+        // ---- entries of up to 32 bins: one lane per bin dedups the ranks of its 4 pixels
+        const int dd = d0 + lane;
+        int r[kPixH];
+#pragma unroll
+        for (int p = 0; p < kPixH; ++p) r[p] = (dd < prm.d) ? s_rank[dd * kJointPad + p * kPixW + warp] : -1;
+        int er[kPixH], em[kPixH], ne = 0;
+        unsigned todo = 0;
+#pragma unroll
+        for (int p = 0; p < kPixH; ++p) todo |= (r[p] >= 0) ? (1u << p) : 0u;
+#pragma unroll
+        for (int p = 0; p < kPixH; ++p) {
+          er[p] = -1; em[p] = 0;
+          if (todo & (1u << p)) {
+            unsigned m = 0;
+#pragma unroll
+            for (int q = p; q < kPixH; ++q) m |= ((todo >> q) & 1u) && r[q] == r[p] ? (1u << q) : 0u;
+            todo &= ~m;
+            er[ne] = r[p]; em[ne] = (int)m; ++ne;   // compacted to the front (ne <= p + 1)
+          }
+        }
+        int incl = ne;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(kFullMask, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int n_ent = __shfl_sync(kFullMask, incl, 31);
+        const int base = incl - ne;
+#pragma unroll
+        for (int k = 0; k < kPixH; ++k)
+          if (k < ne) my_list[base + k] = make_int2(er[k], dd | (em[k] << 16));
+        __syncwarp();
+
+        // ---- 4 entries (<= 16 points) per batch: 4 rows in flight
+        for (int b = 0; b < n_ent; b += 4) {
+          float4 g[4];
+          int meta[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (b + u < n_ent) {                     // warp-uniform
+              const int2 e = my_list[b + u];         // broadcast read
+              meta[u] = e.y;
+              g[u] = Vec4<T>::load(og_lane, (int64_t)e.x * prm.c);
+            } else {
+              meta[u] = 0;
+              g[u] = zero;
+            }
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float v[8];
+#pragma unroll
+            for (int uu = 0; uu < 2; ++uu) {
+              const int u = 2 * half + uu;
+              const int bin = meta[u] & 0xffff;
+#pragma unroll
+              for (int p = 0; p < kPixH; ++p) {
+                float dot = 0.f;
+                if ((meta[u] >> (16 + p)) & 1) {     // warp-uniform
+                  fg[p] = fma4(g[u], s_depth[bin * kJointPad + p * kPixW + warp], fg[p]);
+                  dot = act ? dot4_packed(g[u], fv[p]) : 0.f;
+                }
+                v[uu * 4 + p] = dot;
+              }
+            }
+            // reduce-scatter over lane bits 2,1,0 then 3,4: lane l holds value (l & 7) = (entry uu, pixel p)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float mine = (lane & 4) ? v[k + 4] : v[k];
+              const float send = (lane & 4) ? v[k] : v[k + 4];
+              v[k] = mine + __shfl_xor_sync(kFullMask, send, 4);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const float mine = (lane & 2) ? v[k + 2] : v[k];
+              const float send = (lane & 2) ? v[k] : v[k + 2];
+              v[k] = mine + __shfl_xor_sync(kFullMask, send, 2);
+            }
+            {
+              const float mine = (lane & 1) ? v[1] : v[0];
+              const float send = (lane & 1) ? v[0] : v[1];
+              v[0] = mine + __shfl_xor_sync(kFullMask, send, 1);
+            }
+            v[0] += __shfl_xor_sync(kFullMask, v[0], 8);
+            v[0] += __shfl_xor_sync(kFullMask, v[0], 16);
+            if (lane < 8) {
+              // value index: bit2 selects the upper half (k+4), bit1 (k+2), bit0 (k+1)
+              const int uu = lane >> 2, p = lane & 3;
+              const int m = (uu == 0) ? meta[2 * half] : meta[2 * half + 1];
+              if ((m >> (16 + p)) & 1) {
+                float* slot = s_dg + (m & 0xffff) * kJointPad + p * kPixW + warp;
+                *slot = (cb == 0) ? v[0] : *slot + v[0];
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    // ---- feat_grad of the 4 pixels
+#pragma unroll
+    for (int p = 0; p < kPixH; ++p) {
+      const int hh = h0 + p;
+      if (ww >= prm.w || hh >= prm.h) continue;
+      if (prm.feat_grad_nchw) {
+        if (act) {
+          float* c = s_fg + (4 * lane) * kJointPad + p * kPixW + warp;
+          c[0 * kJointPad] = fg[p].x;
+          c[1 * kJointPad] = fg[p].y;
+          c[2 * kJointPad] = fg[p].z;
+          c[3 * kJointPad] = fg[p].w;
+        }
+      } else if (act) {
+        Vec4<T>::store(feat_grad, ((int64_t)bn * hw + (int64_t)hh * prm.w + ww) * prm.c + lane_c, fg[p]);
+      }
+    }
+    if (prm.feat_grad_nchw) {
+      __syncthreads();
+      const int px = threadIdx.x & 31;
+      const int hh = h0 + (px >> 3), wx = w0 + (px & 7);
+      if (hh < prm.h && wx < prm.w) {
+        const int64_t o0 = ((int64_t)bn * prm.c + 4 * cb) * hw + (int64_t)hh * prm.w + wx;
+        for (int cc = threadIdx.x >> 5; cc < cw; cc += kBwdWarps)
+          Vec4<T>::store1s(feat_grad, o0 + cc * hw, s_fg[cc * kJointPad + px]);
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  // ---- depth_grad of the block, zeros for dropped points included
+  {
+    const int px = threadIdx.x & 31;
+    const int hh = h0 + (px >> 3), wx = w0 + (px & 7);
+    if (hh < prm.h && wx < prm.w) {
+      const int64_t o0 = img_base + (int64_t)hh * prm.w + wx;
+      for (int dd = threadIdx.x >> 5; dd < prm.d; dd += kBwdWarps)
+        Vec4<T>::store1s(depth_grad, o0 + dd * hw, s_dg[dd * kJointPad + px]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 template <typename T, int LAYOUT>
 static int forward_tile_t(const void* depth, const void* feat, void* out, const int* rd, const int* rf,
@@ -557,6 +770,30 @@ static int forward_tile_t(const void* depth, const void* feat, void* out, const 
   const int kFwdThreads = warps * 32;
   kern<<<(unsigned)n_tiles, kFwdThreads, smem, st>>>((const T*)depth, (const T*)feat, (T*)out, rd, rf, rb, vox_pt, prm2,
                                                       tiles_x, tiles_per_frame);
+  count_launch();
+  return launch_status();
+}
+
+template <typename T>
+static int backward_joint_t(const void* og, void* dg, void* fg, const void* depth, const void* feat,
+                            const int* point_rank, BwdParams prm, cudaStream_t st) {
+  prm.blocks_w = (prm.w + kPixW - 1) / kPixW;
+  prm.blocks_h = (prm.h + kPixH - 1) / kPixH;
+  const int64_t n_blocks = (int64_t)prm.bn * prm.blocks_w * prm.blocks_h;
+  if (n_blocks == 0) return 0;
+  if (n_blocks > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
+  const int cw = prm.c < 128 ? prm.c : 128;
+  const size_t smem = sizeof(float) * ((size_t)3 * prm.d * kJointPad + 1 + (prm.feat_grad_nchw ? (size_t)cw * kJointPad : 0)) +
+                      sizeof(int2) * (size_t)kBwdWarps * kJointList + 16;
+  if (smem > 200 * 1024) return BEVPOOL_ERR_BAD_ARG;
+  auto kern = pool_bwd_joint_kernel<T>;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  kern<<<(unsigned)n_blocks, kBwdThreads, smem, st>>>((const T*)og, (const T*)depth, (const T*)feat, point_rank, prm,
+                                                       (T*)dg, (T*)fg);
   count_launch();
   return launch_status();
 }
@@ -644,7 +881,7 @@ extern "C" int bevpool_v2_forward_dense(const void* depth, const void* feat, voi
 
 extern "C" int bevpool_v2_backward_dense(const void* out_grad, void* depth_grad, void* feat_grad, const void* depth,
                                          const void* feat, const int32_t* point_rank, int bn, int d, int h, int w,
-                                         int c, int feat_grad_nchw, int dtype, void* stream) {
+                                         int c, int feat_grad_nchw, int column_hint, int dtype, void* stream) {
   if (bn < 0 || d <= 0 || h < 0 || w < 0) return BEVPOOL_ERR_BAD_ARG;
   if (c <= 0 || c % 4) return BEVPOOL_ERR_BAD_CHANNELS;
   if ((int64_t)bn * h * w == 0) return BEVPOOL_OK;
@@ -659,10 +896,14 @@ extern "C" int bevpool_v2_backward_dense(const void* out_grad, void* depth_grad,
   prm.blocks_w = prm.blocks_h = 0;
   prm.feat_grad_nchw = feat_grad_nchw ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (d >= 65536) return BEVPOOL_ERR_BAD_ARG;
   if (dtype == BEVPOOL_F32)
-    return backward_block_t<float>(out_grad, depth_grad, feat_grad, depth, feat, point_rank, prm, st);
+    return column_hint ? backward_joint_t<float>(out_grad, depth_grad, feat_grad, depth, feat, point_rank, prm, st)
+                       : backward_block_t<float>(out_grad, depth_grad, feat_grad, depth, feat, point_rank, prm, st);
   if (dtype == BEVPOOL_BF16)
-    return backward_block_t<__nv_bfloat16>(out_grad, depth_grad, feat_grad, depth, feat, point_rank, prm, st);
+    return column_hint
+               ? backward_joint_t<__nv_bfloat16>(out_grad, depth_grad, feat_grad, depth, feat, point_rank, prm, st)
+               : backward_block_t<__nv_bfloat16>(out_grad, depth_grad, feat_grad, depth, feat, point_rank, prm, st);
   return BEVPOOL_ERR_BAD_ARG;
 }
 

@@ -192,7 +192,8 @@ class _FusedViewPool(torch.autograd.Function):
         lib = _lib.load()
         _lib.check(lib.bevpool_v2_backward_dense(_ptr(og_cl), _ptr(depth_grad), _ptr(feat_grad), _ptr(depth),
                                                  _ptr(feat_cl), _ptr(pr.point_rank), pr.bn, pr.d, pr.h, pr.w, C, 1,
-                                                 _dtype_code(feat_cl), _stream()), "bevpool_v2_backward_dense")
+                                                 1 if Z == 1 else 0, _dtype_code(feat_cl), _stream()),
+                   "bevpool_v2_backward_dense")
         return depth_grad, feat_grad, None, None
 
 

@@ -38,7 +38,7 @@ def run(s, upto):
     if upto == 4: return og
     dg = torch.empty_like(s["depth"]); fg = torch.empty_like(s["feat"])
     lib.bevpool_v2_backward_dense(og.data_ptr(), dg.data_ptr(), fg.data_ptr(), s["depth"].data_ptr(), fcl.data_ptr(), pr.point_rank.data_ptr(),
-                                  pr.bn, pr.d, pr.h, pr.w, C, 1, bp._dtype_code(fcl), st)
+                                  pr.bn, pr.d, pr.h, pr.w, C, 1, int(os.environ.get('HINT', 1 if Z == 1 else 0)), bp._dtype_code(fcl), st)
     return (out, dg, fg)
 
 def time_prefix(upto, reps=60):
