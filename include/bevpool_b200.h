@@ -134,11 +134,19 @@ int bevpool_voxel_table(const int32_t* ranks_bev_sorted, int64_t n_points, const
  * zeroed): new_zeros + kernel + permute of bev_pool.py:27,29,91 in one pass.
  * ranks_depth / ranks_bev are the sorted per-point lists; ranks_bev must be non-decreasing. ranks_feat may be NULL when it is derivable from ranks_depth, as for every output of
  * voxel_pooling_prepare_v2: rf = (rd / dhw) * hw + rd % hw  (dhw = D*H*W, hw = H*W).
- * The grid is n_frames x rows_per_frame (= Z*Y) x x voxels. */
+ * The grid is n_frames x rows_per_frame (= Z*Y) x x voxels.
+ * n_points: number of sorted points, or an upper bound with the true count in counts_dev[0].
+ * scratch (bevpool_v2_forward_dense_scratch_bytes, 256-byte aligned): the pooled rows are produced
+ * channels-last by a barrier-free streaming kernel (one warp per fixed-size chunk of the sorted point list,
+ * voxels cut by a chunk border finished in chunk order by a fix-up kernel) and, for layout BCZYX, transposed
+ * + zero-filled by a second, bandwidth-bound pass; with no / too little scratch, or c > 128, the single-pass
+ * shared-memory tile kernel is used instead. */
+size_t bevpool_v2_forward_dense_scratch_bytes(int64_t n_points, int64_t n_voxels, int c, int layout, int dtype);
 int bevpool_v2_forward_dense(const void* depth, const void* feat, void* out,
                              const int32_t* ranks_depth, const int32_t* ranks_feat, const int32_t* ranks_bev,
-                             const int32_t* vox_pt, int c, int64_t n_frames, int64_t rows_per_frame, int x, int dhw, int hw,
-                             int layout, int dtype, void* stream);
+                             const int32_t* vox_pt, int64_t n_points, const int32_t* counts_dev,
+                             int c, int64_t n_frames, int64_t rows_per_frame, int x, int dhw, int hw,
+                             int layout, int dtype, void* scratch, size_t scratch_bytes, void* stream);
 
 /* Sort-free backward for rank arrays that came from bevpool_prepare_v2: walks the D depth
  * bins of every feature pixel through point_rank, writes EVERY element of depth_grad

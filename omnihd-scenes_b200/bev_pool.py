@@ -142,12 +142,20 @@ def _launch_voxel_table(rb_sorted, n_points, counts_dev, n_vox_total):
     return vox_pt
 
 
-def _launch_forward_dense(depth, feat, out, rd, rf, rb, vox_pt, frames, rows, x, layout, dhw=0, hw=0):
-    """rf=None: ranks_feat is derived from ranks_depth on the fly (dhw = D*H*W, hw = H*W)."""
+def _launch_forward_dense(depth, feat, out, rd, rf, rb, vox_pt, frames, rows, x, layout, dhw=0, hw=0,
+                          n_points=None, counts_dev=None):
+    """rf=None: ranks_feat is derived from ranks_depth on the fly (dhw = D*H*W, hw = H*W).
+    n_points: sorted-point count (default: len(rd)); with counts_dev it is an upper bound and the true count
+    is read on the device. A scratch buffer is handed to the library for the streaming forward + layout pass."""
     lib = _lib.load()
+    n_points = rd.numel() if n_points is None else n_points
+    c = feat.shape[-1]
+    code = _dtype_code(feat)
+    nbytes = lib.bevpool_v2_forward_dense_scratch_bytes(n_points, frames * rows * x, c, layout, code) if c <= 128 else 0
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=out.device) if nbytes else None
     _lib.check(lib.bevpool_v2_forward_dense(_ptr(depth), _ptr(feat), _ptr(out), _ptr(rd), _ptr(rf), _ptr(rb), _ptr(vox_pt),
-                                            feat.shape[-1], frames, rows, x, dhw, hw, layout, _dtype_code(feat),
-                                            _stream()), "bevpool_v2_forward_dense")
+                                            n_points, _ptr(counts_dev), c, frames, rows, x, dhw, hw, layout, code,
+                                            _ptr(scratch), nbytes, _stream()), "bevpool_v2_forward_dense")
 
 
 def _launch_transpose(src, dst, b, c, zyx, to_channels_last):

@@ -355,6 +355,213 @@ pool_fwd_tile_kernel(const T* __restrict__ depth, const T* __restrict__ feat, T*
   }
 }
 
+// ------------------------------------------------------------------------------------------ forward, streaming
+// The default forward. The grid unit is a fixed-size chunk of the SORTED POINT LIST (perfect balance, work
+// proportional to points, no per-tile cost — the tile kernel above pays ~5 us of latency chains per tile and
+// its heavy tiles near the cameras set the kernel's tail; on sparse occupancy grids that was fatal). One warp
+// per chunk, no barriers: each complete voxel is written as one coalesced channels-last row straight to global
+// memory; voxels cut by a chunk border go through two scratch rows per chunk and are finished in chunk order by
+// chunk_fixup_kernel (fixed summation order, no atomics). Empty voxels are not touched here: the layout pass
+// that follows (cl_to_bczyx_zero_fill_kernel) knows them from vox_pt and writes zeros while it transposes.
+constexpr int kTcCols = 64;
+
+// chunk_sum with global row stores. part_lane = &s_part[item][0][4*lane]; s_col[0..1]: voxel rank of the slots
+// (-1 none; s_col[1] == -2: the chunk lies inside one voxel that continues into the next chunk).
+template <typename T>
+__device__ __forceinline__ void chunk_stream(const T* __restrict__ depth, const T* __restrict__ feat_lane,
+                                             const int* __restrict__ rd, const int* __restrict__ rf,
+                                             const int* __restrict__ rb, int p, int pe, bool head_partial,
+                                             bool tail_partial, const FwdParams& prm, T* __restrict__ out_lane,
+                                             float* part_lane, int* s_col, int cw, bool act) {
+  const int lane = lane_id();
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc = zero;
+  int rd2 = (p + 32 + lane < pe) ? ldg_stream_i32(rd + p + 32 + lane) : 0;
+  int f_n = 0, col_n = 0;
+  float d_n = 0.f;
+  if (p + lane < pe)
+    load_point<T>(depth, rf, rb, ldg_stream_i32(rd + p + lane), p + lane, prm, 0, f_n, d_n, col_n);   // col = voxel rank
+  int cur = __shfl_sync(kFullMask, col_n, 0);
+  int carry = cur;
+  bool first_seg = true;
+
+  auto flush = [&](bool last) {
+    const bool to_part = (first_seg && head_partial) || (last && tail_partial);
+    if (to_part) {
+      // slot 0: continuation of a voxel opened by an earlier chunk; slot 1: voxel opened here, continues later
+      const bool cont = first_seg && head_partial;
+      const int slot = cont ? 0 : 1;
+      if (act) *reinterpret_cast<float4*>(part_lane + slot * cw) = acc;
+      if (lane == 0) {
+        s_col[slot] = cur;
+        if (cont && last && tail_partial) s_col[1] = -2;   // the voxel stays open across this whole chunk
+      }
+    } else if (act) {
+      Vec4<T>::store_keep(out_lane, (int64_t)cur * prm.c, acc);
+    }
+    first_seg = false;
+  };
+
+  for (int q = p; q < pe; q += 32) {
+    const int my_f = f_n, my_col = col_n;
+    const float my_d = d_n;
+    const int rd_next = rd2;
+    rd2 = (q + 64 + lane < pe) ? ldg_stream_i32(rd + q + 64 + lane) : 0;
+    f_n = 0; col_n = 0; d_n = 0.f;
+    if (q + 32 + lane < pe) load_point<T>(depth, rf, rb, rd_next, q + 32 + lane, prm, 0, f_n, d_n, col_n);
+
+    const int n = min(32, pe - q);
+    int prev = __shfl_up_sync(kFullMask, my_col, 1);
+    if (lane == 0) prev = carry;
+    const unsigned bmask = __ballot_sync(kFullMask, lane < n && my_col != prev);
+    carry = __shfl_sync(kFullMask, my_col, n - 1);
+    if (n == 32) {
+#pragma unroll 1
+      for (int i0 = 0; i0 < 32; i0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          v[u] = Vec4<T>::load(feat_lane, (int64_t)__shfl_sync(kFullMask, my_f, i0 + u) * prm.c);
+        const unsigned m8 = (bmask >> i0) & 0xffu;
+        if (m8 == 0) {   // common: the 8 points stay inside the current voxel
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc = fma4(v[u], __shfl_sync(kFullMask, my_d, i0 + u), acc);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float dd = __shfl_sync(kFullMask, my_d, i0 + u);
+            if (m8 & (1u << u)) {
+              flush(false);
+              cur = __shfl_sync(kFullMask, my_col, i0 + u);
+              acc = zero;
+            }
+            acc = fma4(v[u], dd, acc);
+          }
+        }
+      }
+    } else {
+      for (int i0 = 0; i0 < n; i0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int f = __shfl_sync(kFullMask, my_f, i0 + u);
+          v[u] = (i0 + u < n) ? Vec4<T>::load(feat_lane, (int64_t)f * prm.c) : zero;
+        }
+        const unsigned m8 = bmask >> i0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float dd = __shfl_sync(kFullMask, my_d, i0 + u);
+          if (m8 & (1u << u)) {
+            flush(false);
+            cur = __shfl_sync(kFullMask, my_col, i0 + u);
+            acc = zero;
+          }
+          acc = fma4(v[u], dd, acc);
+        }
+      }
+    }
+  }
+  flush(true);
+}
+
+template <typename T, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+pool_fwd_chunk_kernel(const T* __restrict__ depth, const T* __restrict__ feat, T* __restrict__ out_cl,
+                      const int* __restrict__ rd, const int* __restrict__ rf, const int* __restrict__ rb,
+                      const int* __restrict__ counts_dev, int n_points, int chunk, FwdParams prm,
+                      float* __restrict__ part /*[chunks][2][c]*/, int* __restrict__ part_rank /*[chunks][2]*/) {
+  const int lane = lane_id();
+  const int c4 = prm.c >> 2;
+  if (counts_dev) n_points = counts_dev[0];
+  const int64_t cidx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t p64 = cidx * chunk;
+  if (p64 >= n_points) return;
+  const int p = (int)p64, pe = min(n_points, p + chunk);
+  const bool head_partial = p > 0 && __ldg(rb + p - 1) == __ldg(rb + p);
+  const bool tail_partial = pe < n_points && __ldg(rb + pe) == __ldg(rb + pe - 1);
+  int* my_rank = part_rank + cidx * 2;
+  if (lane < 2) my_rank[lane] = -1;
+  __syncwarp();
+  const bool act = lane < c4;
+  const int lane_c = 4 * min(lane, c4 - 1);
+  chunk_stream<T>(depth, feat + lane_c, rd, rf, rb, p, pe, head_partial, tail_partial, prm, out_cl + lane_c,
+                  part + cidx * 2 * prm.c + 4 * lane, my_rank, prm.c, act);
+}
+
+// One warp per chunk whose tail slot opens a cut voxel: adds the following chunks' head slots in order.
+template <typename T>
+__global__ void __launch_bounds__(256)
+chunk_fixup_kernel(const float* __restrict__ part, const int* __restrict__ part_rank, const int* __restrict__ counts_dev,
+                   int n_points, int chunk, int c, T* __restrict__ out_cl) {
+  if (counts_dev) n_points = counts_dev[0];
+  const int64_t n_chunks = ((int64_t)n_points + chunk - 1) / chunk;
+  const int lane = lane_id();
+  const int64_t cidx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (cidx >= n_chunks) return;
+  const int open = part_rank[cidx * 2 + 1];
+  if (open < 0) return;
+  for (int ch = 4 * lane; ch < c; ch += 128) {
+    float4 acc = *reinterpret_cast<const float4*>(part + (cidx * 2 + 1) * c + ch);
+    for (int64_t j = cidx + 1; j < n_chunks; ++j) {
+      const float4 pv = *reinterpret_cast<const float4*>(part + (j * 2) * c + ch);
+      acc.x += pv.x; acc.y += pv.y; acc.z += pv.z; acc.w += pv.w;
+      if (part_rank[j * 2 + 1] != -2) break;   // the voxel ends inside chunk j
+    }
+    Vec4<T>::store_keep(out_cl, (int64_t)open * c + ch, acc);
+  }
+}
+
+// [B][V][C] channels-last rows of the NON-EMPTY voxels -> [B][C][V], zeros for empty voxels (known from
+// vox_pt). A CTA moves all channels of 64 consecutive voxels: 128-bit coalesced on both sides.
+template <typename T>
+__global__ void __launch_bounds__(256)
+cl_to_bczyx_zero_fill_kernel(const T* __restrict__ src_cl, const int* __restrict__ vox_pt, T* __restrict__ dst,
+                             int c, int64_t vpf, int64_t tiles_per_frame) {
+  extern __shared__ float t[];            // [c][kTcCols + 1]
+  __shared__ int s_pt[kTcCols + 1];
+  const int64_t b = blockIdx.x / tiles_per_frame;
+  const int64_t v0 = (blockIdx.x % tiles_per_frame) * kTcCols;
+  const int ncol = (int)min((int64_t)kTcCols, vpf - v0);
+  const int64_t rank0 = b * vpf + v0;
+  for (int i = threadIdx.x; i <= ncol; i += 256) s_pt[i] = __ldg(vox_pt + rank0 + i);
+  __syncthreads();
+  const int c4 = c >> 2;
+  for (int i = threadIdx.x; i < ncol * c4; i += 256) {
+    const int col = i / c4, q = i - col * c4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s_pt[col + 1] > s_pt[col]) v = Vec4<T>::load_stream(src_cl, (rank0 + col) * c + 4 * q);
+    float* o = t + (4 * q) * (kTcCols + 1) + col;
+    o[0] = v.x; o[kTcCols + 1] = v.y; o[2 * (kTcCols + 1)] = v.z; o[3 * (kTcCols + 1)] = v.w;
+  }
+  __syncthreads();
+  T* d = dst + (b * c) * vpf + v0;
+  const bool vec = ncol == kTcCols && (vpf & 3) == 0 && ((((uintptr_t)dst) & 15) == 0);
+  if (vec) {
+    for (int i = threadIdx.x; i < c * (kTcCols / 4); i += 256) {
+      const int ch = i / (kTcCols / 4), q = i % (kTcCols / 4);
+      const float* p = t + ch * (kTcCols + 1) + 4 * q;
+      Vec4<T>::store(d, (int64_t)ch * vpf + 4 * q, make_float4(p[0], p[1], p[2], p[3]));
+    }
+  } else {
+    for (int i = threadIdx.x; i < c * kTcCols; i += 256) {
+      const int ch = i / kTcCols, q = i % kTcCols;
+      if (q < ncol) Vec4<T>::store1s(d, (int64_t)ch * vpf + q, t[ch * (kTcCols + 1) + q]);
+    }
+  }
+}
+
+// channels-last final layout: rows of empty voxels are zeroed (the streaming forward writes the others)
+template <typename T>
+__global__ void __launch_bounds__(256)
+zero_empty_rows_kernel(T* __restrict__ out_cl, const int* __restrict__ vox_pt, int c, int64_t n_voxels) {
+  const int c4 = c >> 2;
+  const int64_t total = n_voxels * c4;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t v = i / c4;
+    if (__ldg(vox_pt + v + 1) == __ldg(vox_pt + v)) Vec4<T>::store(out_cl, i * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+}
+
 // ------------------------------------------------------------------------------------------ backward
 constexpr int kPixW = 8, kPixH = 4, kPixBlock = kPixW * kPixH;   // 32 pixels per CTA
 constexpr int kBwdWarps = 8;
@@ -774,6 +981,58 @@ static int forward_tile_t(const void* depth, const void* feat, void* out, const 
   return launch_status();
 }
 
+static const int kFwdChunkMin = 64;   // smallest chunk the scratch is sized for
+
+// Streaming forward + layout pass. `scratch` (n_voxels*c elements of T) holds the channels-last rows when the
+// requested layout is BCZYX; for BZYXC the rows go straight to `out` and empty rows are zeroed.
+template <typename T>
+static int forward_stream_t(const void* depth, const void* feat, void* out, const int* rd, const int* rf,
+                            const int* rb, const int* vox_pt, const FwdParams& prm, int layout, void* scratch,
+                            const int* counts_dev, int64_t n_points_upper, float* part, int* part_rank,
+                            cudaStream_t st) {
+  static int chunk_env = -1, minb_env = 3;
+  if (chunk_env < 0) {
+    const char* e;
+    chunk_env = (e = getenv("BEVPOOL_FWD_CHUNK")) ? atoi(e) : 128;
+    if (chunk_env > 0 && chunk_env < kFwdChunkMin) chunk_env = kFwdChunkMin;
+    minb_env = (e = getenv("BEVPOOL_FWD_MINB")) ? atoi(e) : 3;
+  }
+  T* rows_dst0 = (T*)(layout == BEVPOOL_LAYOUT_BCZYX ? scratch : out);
+  if (chunk_env <= 0) chunk_env = 128;
+  {
+    const int64_t n_chunks = ((int64_t)n_points_upper + chunk_env - 1) / chunk_env;
+    if (n_chunks > 0) {
+      const unsigned blocks = (unsigned)((n_chunks + 7) / 8);
+      if (minb_env >= 4)
+        pool_fwd_chunk_kernel<T, 4><<<blocks, 256, 0, st>>>((const T*)depth, (const T*)feat, rows_dst0, rd, rf, rb, counts_dev,
+                                                             (int)n_points_upper, chunk_env, prm, part, part_rank);
+      else
+        pool_fwd_chunk_kernel<T, 3><<<blocks, 256, 0, st>>>((const T*)depth, (const T*)feat, rows_dst0, rd, rf, rb, counts_dev,
+                                                             (int)n_points_upper, chunk_env, prm, part, part_rank);
+      chunk_fixup_kernel<T><<<blocks, 256, 0, st>>>(part, part_rank, counts_dev, (int)n_points_upper, chunk_env, prm.c, rows_dst0);
+      count_launch(2);
+    }
+  }
+  const int64_t vpf = prm.rows * prm.x, n_vox = vpf * prm.frames;
+  if (layout == BEVPOOL_LAYOUT_BCZYX) {
+    const int64_t tpf = (vpf + kTcCols - 1) / kTcCols;
+    const size_t smem2 = sizeof(float) * (size_t)prm.c * (kTcCols + 1);
+    static size_t attr2 = 0;
+    if (smem2 > 48 * 1024 && smem2 > attr2) {
+      cudaFuncSetAttribute(cl_to_bczyx_zero_fill_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      attr2 = smem2;
+    }
+    cl_to_bczyx_zero_fill_kernel<T><<<(unsigned)(tpf * prm.frames), 256, smem2, st>>>((const T*)scratch, vox_pt, (T*)out,
+                                                                                      prm.c, vpf, tpf);
+  } else {
+    int64_t blocks = (n_vox * (prm.c >> 2) + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    zero_empty_rows_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((T*)out, vox_pt, prm.c, n_vox);
+  }
+  count_launch();
+  return launch_status();
+}
+
 template <typename T>
 static int backward_joint_t(const void* og, void* dg, void* fg, const void* depth, const void* feat,
                             const int* point_rank, BwdParams prm, cudaStream_t st) {
@@ -839,15 +1098,26 @@ extern "C" int bevpool_voxel_table(const int32_t* ranks_bev_sorted, int64_t n_po
   return launch_status();
 }
 
+extern "C" size_t bevpool_v2_forward_dense_scratch_bytes(int64_t n_points, int64_t n_voxels, int c, int layout,
+                                                         int dtype) {
+  if (n_points < 0 || n_voxels < 0 || c <= 0) return 0;
+  const size_t esz = dtype == BEVPOOL_BF16 ? 2 : 4;
+  size_t rows = layout == BEVPOOL_LAYOUT_BCZYX ? (size_t)n_voxels * c * esz : 0;
+  rows = (rows + 255) / 256 * 256;
+  const size_t n_chunks = (size_t)(n_points + kFwdChunkMin - 1) / kFwdChunkMin + 1;
+  return rows + n_chunks * 2 * (size_t)c * sizeof(float) + n_chunks * 2 * sizeof(int) + 256;
+}
+
 extern "C" int bevpool_v2_forward_dense(const void* depth, const void* feat, void* out, const int32_t* ranks_depth,
                                         const int32_t* ranks_feat, const int32_t* ranks_bev, const int32_t* vox_pt,
-                                        int c, int64_t n_frames,
+                                        int64_t n_points, const int32_t* counts_dev, int c, int64_t n_frames,
                                         int64_t rows_per_frame, int x, int dhw, int hw, int layout, int dtype,
-                                        void* stream) {
-  if (n_frames < 0 || rows_per_frame < 0 || x < 0) return BEVPOOL_ERR_BAD_ARG;
+                                        void* scratch, size_t scratch_bytes, void* stream) {
+  if (n_frames < 0 || rows_per_frame < 0 || x < 0 || n_points < 0 || n_points >= INT32_MAX) return BEVPOOL_ERR_BAD_ARG;
   if (c <= 0 || c % 4) return BEVPOOL_ERR_BAD_CHANNELS;
-  if (n_frames * rows_per_frame * x == 0) return BEVPOOL_OK;
-  if (n_frames * rows_per_frame * x >= INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
+  const int64_t n_vox = n_frames * rows_per_frame * x;
+  if (n_vox == 0) return BEVPOOL_OK;
+  if (n_vox >= INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
   if (!depth || !feat || !out || !ranks_depth || !ranks_bev || !vox_pt) return BEVPOOL_ERR_BAD_ARG;
   if (!ranks_feat && (dhw <= 0 || hw <= 0)) return BEVPOOL_ERR_BAD_ARG;
   if (layout != BEVPOOL_LAYOUT_BZYXC && layout != BEVPOOL_LAYOUT_BCZYX) return BEVPOOL_ERR_BAD_ARG;
@@ -857,6 +1127,7 @@ extern "C" int bevpool_v2_forward_dense(const void* depth, const void* feat, voi
   prm.x = x;
   prm.rows = rows_per_frame;
   prm.frames = n_frames;
+  prm.chunks_per_warp = 1;
   prm.dhw = dhw > 0 ? dhw : 1;
   prm.hw = hw > 0 ? hw : 1;
   {  // rd / dhw == (rd * mul) >> shift for 0 <= rd < 2^31 (round-up magic number)
@@ -866,6 +1137,27 @@ extern "C" int bevpool_v2_forward_dense(const void* depth, const void* feat, voi
     prm.dhw_mul = (uint32_t)((((uint64_t)1 << (31 + s)) / (uint64_t)prm.dhw) + 1);
   }
   cudaStream_t st = (cudaStream_t)stream;
+  static int use_stream = -1;
+  if (use_stream < 0) {
+    const char* e = getenv("BEVPOOL_FWD_KERNEL");   // "tile" selects the shared-memory tile kernel (A/B testing)
+    use_stream = !(e && e[0] == 't');
+  }
+  const size_t need = bevpool_v2_forward_dense_scratch_bytes(n_points, n_vox, c, layout, dtype);
+  if (use_stream && c <= 128 && scratch && scratch_bytes >= need && ((uintptr_t)scratch % 256) == 0) {
+    const size_t esz = dtype == BEVPOOL_BF16 ? 2 : 4;
+    size_t rows = layout == BEVPOOL_LAYOUT_BCZYX ? (size_t)n_vox * c * esz : 0;
+    rows = (rows + 255) / 256 * 256;
+    const size_t n_chunks = (size_t)(n_points + kFwdChunkMin - 1) / kFwdChunkMin + 1;
+    float* part = (float*)((char*)scratch + rows);
+    int* part_rank = (int*)((char*)scratch + rows + n_chunks * 2 * (size_t)c * sizeof(float));
+    if (dtype == BEVPOOL_F32)
+      return forward_stream_t<float>(depth, feat, out, ranks_depth, ranks_feat, ranks_bev, vox_pt, prm, layout, scratch,
+                                     counts_dev, n_points, part, part_rank, st);
+    if (dtype == BEVPOOL_BF16)
+      return forward_stream_t<__nv_bfloat16>(depth, feat, out, ranks_depth, ranks_feat, ranks_bev, vox_pt, prm, layout,
+                                             scratch, counts_dev, n_points, part, part_rank, st);
+    return BEVPOOL_ERR_BAD_ARG;
+  }
 #define DISPATCH(T, L) return forward_tile_t<T, L>(depth, feat, out, ranks_depth, ranks_feat, ranks_bev, vox_pt, prm, st)
   if (dtype == BEVPOOL_F32) {
     if (layout == BEVPOOL_LAYOUT_BCZYX) DISPATCH(float, BEVPOOL_LAYOUT_BCZYX);

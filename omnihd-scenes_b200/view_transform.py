@@ -174,7 +174,7 @@ class _FusedViewPool(torch.autograd.Function):
         vox_pt = _launch_voxel_table(pr.rb, pr.p0, pr.counts, B * Z * Y * X)
         out = feat.new_empty((B, C, Z, Y, X))
         _launch_forward_dense(depth, feat_cl, out, pr.rd, None, pr.rb, vox_pt, B, Z * Y, X, _lib.LAYOUT_BCZYX,
-                              dhw=pr.d * pr.hw, hw=pr.hw)
+                              dhw=pr.d * pr.hw, hw=pr.hw, n_points=pr.p0, counts_dev=pr.counts)
         ctx.prepared, ctx.shape, ctx.feat_shape = pr, shape, feat.shape
         ctx.save_for_backward(depth, feat_cl)
         return out

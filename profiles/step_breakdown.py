@@ -32,7 +32,7 @@ def run(s, upto):
     tab = bp._launch_voxel_table(pr.rb, pr.p0, pr.counts, V)
     if upto == 2: return tab
     out = s["feat"].new_empty((B, C, Z, Y, X))
-    bp._launch_forward_dense(s["depth"], fcl, out, pr.rd, None, pr.rb, tab, B, Z * Y, X, pkg._lib.LAYOUT_BCZYX, dhw=D * H * W, hw=H * W)
+    bp._launch_forward_dense(s["depth"], fcl, out, pr.rd, None, pr.rb, tab, B, Z * Y, X, pkg._lib.LAYOUT_BCZYX, dhw=D * H * W, hw=H * W, n_points=pr.p0, counts_dev=pr.counts)
     if upto == 3: return out
     og = s["gout"].new_empty((B, Z, Y, X, C)); bp._launch_transpose(s["gout"], og, B, C, Z * Y * X, True)
     if upto == 4: return og

@@ -1,4 +1,7 @@
-for cfgs in "8 2 1" "8 1 1" "16 2 1" "16 1 1" "16 2 2" "16 1 2" "8 2 2" "4 2 1" "12 2 1"; do
+for cfgs in "128 3" "128 4" "64 3" "256 3" "256 4" "512 3" "0 3"; do
   set -- $cfgs
-  WHICH=fwd BEVPOOL_FWD_WARPS=$1 BEVPOOL_FWD_CPW=$2 BEVPOOL_FWD_MINB=$3 python profiles/time_kernels.py 2>&1 | tail -1
+  echo "chunk=$1 minb=$2: $(BEVPOOL_FWD_CHUNK=$1 BEVPOOL_FWD_MINB=$2 python profiles/step_breakdown.py 2>&1 | tail -1 | cut -c40-320)"
 done
+echo "tile: $(BEVPOOL_FWD_KERNEL=tile python profiles/step_breakdown.py 2>&1 | tail -1 | cut -c40-320)"
+echo "occ chunk128: $(python profiles/step_breakdown.py occ_200x200x16_b64 4 2>&1 | tail -1 | cut -c40-320)"
+echo "hires chunk128: $(python profiles/step_breakdown.py bevdepth_hires_b16 4 2>&1 | tail -1 | cut -c40-320)"

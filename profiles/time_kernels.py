@@ -30,7 +30,7 @@ code = bp._dtype_code(sets[0]["fcl"])
 st = torch.cuda.current_stream().cuda_stream
 def fwd(i):
     s = sets[i % NS]; p = s["pr"]
-    bp._launch_forward_dense(s["depth"], s["fcl"], s["out"], p.rd, None, p.rb, s["tab"], B, Z * Y, X, pkg._lib.LAYOUT_BCZYX, dhw=D * H * W, hw=H * W)
+    bp._launch_forward_dense(s["depth"], s["fcl"], s["out"], p.rd, None, p.rb, s["tab"], B, Z * Y, X, pkg._lib.LAYOUT_BCZYX, dhw=D * H * W, hw=H * W, n_points=p.p0, counts_dev=p.counts)
 def bwd(i):
     s = sets[i % NS]; p = s["pr"]
     lib.bevpool_v2_backward_dense(s["og"].data_ptr(), s["dg"].data_ptr(), s["fg"].data_ptr(), s["depth"].data_ptr(), s["fcl"].data_ptr(),

@@ -405,5 +405,5 @@ def test_errors_are_loud(pkg):
     lib = pkg._lib.load()
     assert lib.bevpool_v2_forward(0, 0, 0, 0, 0, 0, 0, 0, 5, 5, 8, 0, 0) == -1
     assert lib.bevpool_v2_forward(0, 0, 0, 0, 0, 0, 0, 0, 5, 5, 0, 0, 0) == -2
-    assert lib.bevpool_v2_forward_dense(16, 16, 16, 16, 0, 16, 16, 6, 1, 8, 8, 0, 0, 1, 0, 0) == -2     # C % 4
-    assert lib.bevpool_v2_forward_dense(16, 16, 16, 16, 0, 16, 16, 8, 1, 8, 8, 0, 0, 1, 0, 0) == -1     # no ranks_feat, no dims
+    assert lib.bevpool_v2_forward_dense(16, 16, 16, 16, 0, 16, 16, 5, 0, 6, 1, 8, 8, 0, 0, 1, 0, 0, 0, 0) == -2     # C % 4
+    assert lib.bevpool_v2_forward_dense(16, 16, 16, 16, 0, 16, 16, 5, 0, 8, 1, 8, 8, 0, 0, 1, 0, 0, 0, 0) == -1     # no ranks_feat, no dims
