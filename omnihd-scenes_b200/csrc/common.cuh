@@ -74,6 +74,7 @@ struct Vec4<float> {
   static __device__ __forceinline__ void store_keep(float* base, int64_t elem, float4 v) {
     *reinterpret_cast<float4*>(base + elem) = v;
   }
+  static __device__ __forceinline__ float4 load_smem(const float* p) { return *reinterpret_cast<const float4*>(p); }
   static __device__ __forceinline__ float load1(const float* base, int64_t elem) { return __ldg(base + elem); }
   static __device__ __forceinline__ void store1(float* base, int64_t elem, float v) { base[elem] = v; }
   static __device__ __forceinline__ void store1s(float* base, int64_t elem, float v) { stg_stream_f32(base + elem, v); }
@@ -111,6 +112,9 @@ struct Vec4<__nv_bfloat16> {
     r.x = *reinterpret_cast<uint32_t*>(&lo);
     r.y = *reinterpret_cast<uint32_t*>(&hi);
     *reinterpret_cast<uint2*>(base + elem) = r;
+  }
+  static __device__ __forceinline__ float4 load_smem(const __nv_bfloat16* p) {
+    return unpack(*reinterpret_cast<const uint2*>(p));
   }
   static __device__ __forceinline__ float load1(const __nv_bfloat16* base, int64_t elem) {
     return __bfloat162float(base[elem]);

@@ -737,6 +737,17 @@ pool_bwd_block_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
 constexpr int kJointPad = kPixBlock + 1;   // row stride of the staged [d][pixel] arrays (conflict-free by bin)
 constexpr int kJointList = 128;            // list entries per 32-bin round: 4 pixels x 32 bins
 
+constexpr int kJointRows = 16;   // out_grad rows a warp keeps in flight (cp.async into shared memory)
+
+template <typename T>
+__device__ __forceinline__ void cp_async_chunk(void* smem_dst, const T* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (sizeof(T) == 4)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBwdThreads, 3)
 pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, const T* __restrict__ feat,
@@ -747,8 +758,10 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
   float* s_depth = reinterpret_cast<float*>(smem_raw) + (size_t)prm.d * kJointPad;   // [d][33]
   float* s_dg = s_depth + (size_t)prm.d * kJointPad;                                 // [d][33]
   int2* s_list = reinterpret_cast<int2*>(                                            // [8 warps][128] {rank, bin | mask << 16}
-      (reinterpret_cast<uintptr_t>(s_dg + (size_t)prm.d * kJointPad) + 7) & ~(uintptr_t)7);
-  float* s_fg = reinterpret_cast<float*>(s_list + (size_t)kBwdWarps * kJointList);   // [cw][33] (NCHW output only)
+      (reinterpret_cast<uintptr_t>(s_dg + (size_t)prm.d * kJointPad) + 15) & ~(uintptr_t)15);
+  // [8 warps][16 rows][cw] staged out_grad rows; re-used as the [cw][33] feat_grad transpose tile at the end
+  float* s_rows_f = reinterpret_cast<float*>(s_list + (size_t)kBwdWarps * kJointList);   // row stride: cw floats
+  float* s_fg = s_rows_f;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const int c4 = prm.c >> 2;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -761,26 +774,42 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
   const int h0 = bh * kPixH, w0 = bw * kPixW;
   const int64_t hw = (int64_t)prm.h * prm.w;
   const int64_t img_base = (int64_t)bn * prm.d * hw;
+  unsigned long long t_s = 0, t_a = 0, t_b = 0;
+  if (g_fwd_timeline_on && threadIdx.x == 0) t_s = globaltimer_ns();
 
-  // ---- stage point_rank / depth of the block: 8 consecutive w = one 32-byte sector per (d, h)
+  // ---- stage point_rank / depth of the block: 8 consecutive w = one 32-byte sector per (d, h);
+  //      8 bins per thread are loaded before anything is stored (one memory latency, not eight)
   {
     const int px = threadIdx.x & 31;
-    const int hh = h0 + (px >> 3), ww = w0 + (px & 7);
-    const bool in = hh < prm.h && ww < prm.w;
-    const int64_t o0 = img_base + (int64_t)hh * prm.w + ww;
-    for (int dd = threadIdx.x >> 5; dd < prm.d; dd += kBwdWarps) {
-      int r = -1;
-      float dv = 0.f;
-      if (in) {
-        r = ldg_stream_i32(point_rank + o0 + dd * hw);
-        dv = Vec4<T>::load1(depth, o0 + dd * hw);   // unconditional: no load-to-load dependency
+    const int hh = h0 + (px >> 3), wx = w0 + (px & 7);
+    const bool in = hh < prm.h && wx < prm.w;
+    const int64_t o0 = img_base + (int64_t)hh * prm.w + wx;
+    for (int d0 = 0; d0 < prm.d; d0 += 8 * kBwdWarps) {
+      int r[8];
+      float dv[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int dd = d0 + k * kBwdWarps + warp;
+        r[k] = -1;
+        dv[k] = 0.f;
+        if (in && dd < prm.d) {
+          r[k] = ldg_stream_i32(point_rank + o0 + dd * hw);
+          dv[k] = Vec4<T>::load1(depth, o0 + dd * hw);
+        }
       }
-      s_rank[dd * kJointPad + px] = r;
-      s_depth[dd * kJointPad + px] = dv;
-      s_dg[dd * kJointPad + px] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int dd = d0 + k * kBwdWarps + warp;
+        if (dd < prm.d) {
+          s_rank[dd * kJointPad + px] = r[k];
+          s_depth[dd * kJointPad + px] = dv[k];
+          s_dg[dd * kJointPad + px] = 0.f;
+        }
+      }
     }
   }
   __syncthreads();
+  if (g_fwd_timeline_on && threadIdx.x == 0) t_a = globaltimer_ns();
 
   int2* my_list = s_list + (size_t)warp * kJointList;
   const int ww = w0 + warp;   // this warp's image column; its pixels are px = hl*8 + warp, hl = 0..3
@@ -789,6 +818,7 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
     const int cw = min(prm.c - 4 * cb, 128);
     const int lane_c = 4 * (cb + min(lane, c4 - 1 - cb));
     const T* og_lane = og + lane_c;
+    float* my_rows = s_rows_f + (size_t)warp * kJointRows * cw + 4 * min(lane, c4 - 1 - cb);   // this lane's 16-byte slot
     float4 fv[kPixH], fg[kPixH];
 #pragma unroll
     for (int p = 0; p < kPixH; ++p) {
@@ -804,19 +834,29 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
         int r[kPixH];
 #pragma unroll
         for (int p = 0; p < kPixH; ++p) r[p] = (dd < prm.d) ? s_rank[dd * kJointPad + p * kPixW + warp] : -1;
-        int er[kPixH], em[kPixH], ne = 0;
         unsigned todo = 0;
 #pragma unroll
         for (int p = 0; p < kPixH; ++p) todo |= (r[p] >= 0) ? (1u << p) : 0u;
+        // unique ranks in pixel order; slot k of this lane = k-th distinct rank
+        int er[kPixH], em[kPixH];
+        int ne = 0;
 #pragma unroll
         for (int p = 0; p < kPixH; ++p) {
-          er[p] = -1; em[p] = 0;
+          er[p] = -1;
+          em[p] = 0;
+        }
+#pragma unroll
+        for (int p = 0; p < kPixH; ++p) {
           if (todo & (1u << p)) {
             unsigned m = 0;
 #pragma unroll
-            for (int q = p; q < kPixH; ++q) m |= ((todo >> q) & 1u) && r[q] == r[p] ? (1u << q) : 0u;
+            for (int q = p; q < kPixH; ++q) m |= (((todo >> q) & 1u) && r[q] == r[p]) ? (1u << q) : 0u;
             todo &= ~m;
-            er[ne] = r[p]; em[ne] = (int)m; ++ne;   // compacted to the front (ne <= p + 1)
+            // write into slot `ne` without dynamic register indexing
+#pragma unroll
+            for (int k = 0; k < kPixH; ++k)
+              if (k == ne) { er[k] = r[p]; em[k] = (int)m; }
+            ++ne;
           }
         }
         int incl = ne;
@@ -832,73 +872,63 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
           if (k < ne) my_list[base + k] = make_int2(er[k], dd | (em[k] << 16));
         __syncwarp();
 
-        // ---- 4 entries (<= 16 points) per batch: 4 rows in flight
-        for (int b = 0; b < n_ent; b += 4) {
-          float4 g[4];
-          int meta[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (b + u < n_ent) {                     // warp-uniform
-              const int2 e = my_list[b + u];         // broadcast read
-              meta[u] = e.y;
-              g[u] = Vec4<T>::load(og_lane, (int64_t)e.x * prm.c);
+        // ---- groups of 16 entries: all their out_grad rows are in flight at once (cp.async), then consumed.
+        //      Each lane overwrites the 16 bytes it consumed with its 4 partial dot products, so the cross-lane
+        //      sums are done afterwards by a transposed read (lane = (entry, pixel)) instead of shuffle trees.
+        const int nact = min(32, c4 - cb);
+        for (int g0 = 0; g0 < n_ent; g0 += kJointRows) {
+          const int ng = min(kJointRows, n_ent - g0);
+          for (int e = 0; e < ng; ++e)
+            cp_async_chunk<T>(reinterpret_cast<T*>(my_rows + (size_t)e * cw), og_lane + (int64_t)my_list[g0 + e].x * prm.c);
+          asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+          // each lane reads back only the bytes it copied itself: no warp barrier needed here
+#pragma unroll 2
+          for (int e = 0; e < ng; ++e) {
+            const int meta = my_list[g0 + e].y;
+            float* slot = my_rows + (size_t)e * cw;
+            const float4 g = Vec4<T>::load_smem(reinterpret_cast<const T*>(slot));
+            const float* dp = s_depth + (meta & 0xffff) * kJointPad + warp;
+            float4 d4;
+            if ((meta >> 16) == 0xF) {   // warp-uniform, the common case on Z == 1 grids
+              fg[0] = fma4(g, dp[0 * kPixW], fg[0]);
+              fg[1] = fma4(g, dp[1 * kPixW], fg[1]);
+              fg[2] = fma4(g, dp[2 * kPixW], fg[2]);
+              fg[3] = fma4(g, dp[3 * kPixW], fg[3]);
+              d4 = make_float4(dot4_packed(g, fv[0]), dot4_packed(g, fv[1]), dot4_packed(g, fv[2]), dot4_packed(g, fv[3]));
             } else {
-              meta[u] = 0;
-              g[u] = zero;
-            }
-          }
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float v[8];
-#pragma unroll
-            for (int uu = 0; uu < 2; ++uu) {
-              const int u = 2 * half + uu;
-              const int bin = meta[u] & 0xffff;
+              float dd[kPixH];
 #pragma unroll
               for (int p = 0; p < kPixH; ++p) {
-                float dot = 0.f;
-                if ((meta[u] >> (16 + p)) & 1) {     // warp-uniform
-                  fg[p] = fma4(g[u], s_depth[bin * kJointPad + p * kPixW + warp], fg[p]);
-                  dot = act ? dot4_packed(g[u], fv[p]) : 0.f;
+                dd[p] = 0.f;
+                if ((meta >> (16 + p)) & 1) {
+                  fg[p] = fma4(g, dp[p * kPixW], fg[p]);
+                  dd[p] = dot4_packed(g, fv[p]);
                 }
-                v[uu * 4 + p] = dot;
               }
+              d4 = make_float4(dd[0], dd[1], dd[2], dd[3]);
             }
-            // reduce-scatter over lane bits 2,1,0 then 3,4: lane l holds value (l & 7) = (entry uu, pixel p)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float mine = (lane & 4) ? v[k + 4] : v[k];
-              const float send = (lane & 4) ? v[k] : v[k + 4];
-              v[k] = mine + __shfl_xor_sync(kFullMask, send, 4);
-            }
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const float mine = (lane & 2) ? v[k + 2] : v[k];
-              const float send = (lane & 2) ? v[k] : v[k + 2];
-              v[k] = mine + __shfl_xor_sync(kFullMask, send, 2);
-            }
-            {
-              const float mine = (lane & 1) ? v[1] : v[0];
-              const float send = (lane & 1) ? v[0] : v[1];
-              v[0] = mine + __shfl_xor_sync(kFullMask, send, 1);
-            }
-            v[0] += __shfl_xor_sync(kFullMask, v[0], 8);
-            v[0] += __shfl_xor_sync(kFullMask, v[0], 16);
-            if (lane < 8) {
-              // value index: bit2 selects the upper half (k+4), bit1 (k+2), bit0 (k+1)
-              const int uu = lane >> 2, p = lane & 3;
-              const int m = (uu == 0) ? meta[2 * half] : meta[2 * half + 1];
-              if ((m >> (16 + p)) & 1) {
-                float* slot = s_dg + (m & 0xffff) * kJointPad + p * kPixW + warp;
-                *slot = (cb == 0) ? v[0] : *slot + v[0];
-              }
+            if (act) *reinterpret_cast<float4*>(slot) = d4;
+          }
+          __syncwarp();
+          // value v = (entry, pixel): sum the partials of the active lanes, write depth_grad's staging slot
+          for (int v = lane; v < 4 * ng; v += 32) {
+            const int e = v >> 2, pz = v & 3;
+            const int meta = my_list[g0 + e].y;
+            if ((meta >> (16 + pz)) & 1) {
+              const float* src = s_rows_f + ((size_t)warp * kJointRows + e) * cw + pz;
+              float sum = 0.f;
+              for (int l = 0; l < nact; ++l) sum += src[4 * l];
+              float* out_slot = s_dg + (meta & 0xffff) * kJointPad + pz * kPixW + warp;
+              *out_slot = (cb == 0) ? sum : *out_slot + sum;
             }
           }
+          __syncwarp();
         }
         __syncwarp();
       }
     }
     // ---- feat_grad of the 4 pixels
+    if (prm.feat_grad_nchw) __syncthreads();   // every warp is done with its row buffer: re-use it as s_fg
 #pragma unroll
     for (int p = 0; p < kPixH; ++p) {
       const int hh = h0 + p;
@@ -928,6 +958,7 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
     }
   }
   __syncthreads();
+  if (g_fwd_timeline_on && threadIdx.x == 0) t_b = globaltimer_ns();
   // ---- depth_grad of the block, zeros for dropped points included
   {
     const int px = threadIdx.x & 31;
@@ -937,6 +968,16 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
       for (int dd = threadIdx.x >> 5; dd < prm.d; dd += kBwdWarps)
         Vec4<T>::store1s(depth_grad, o0 + dd * hw, s_dg[dd * kJointPad + px]);
     }
+  }
+  if (g_fwd_timeline_on && threadIdx.x == 0 && blk < 8192) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    g_fwd_timeline[8 * blk + 0] = 0;
+    g_fwd_timeline[8 * blk + 1] = smid;
+    g_fwd_timeline[8 * blk + 2] = t_s;
+    g_fwd_timeline[8 * blk + 3] = globaltimer_ns();
+    g_fwd_timeline[8 * blk + 4] = t_a;
+    g_fwd_timeline[8 * blk + 5] = t_b;
   }
 }
 
@@ -1042,8 +1083,11 @@ static int backward_joint_t(const void* og, void* dg, void* fg, const void* dept
   if (n_blocks == 0) return 0;
   if (n_blocks > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
   const int cw = prm.c < 128 ? prm.c : 128;
-  const size_t smem = sizeof(float) * ((size_t)3 * prm.d * kJointPad + 1 + (prm.feat_grad_nchw ? (size_t)cw * kJointPad : 0)) +
-                      sizeof(int2) * (size_t)kBwdWarps * kJointList + 16;
+  size_t rows_bytes = sizeof(float) * (size_t)kBwdWarps * kJointRows * cw;
+  const size_t fg_bytes = prm.feat_grad_nchw ? sizeof(float) * (size_t)cw * kJointPad : 0;
+  if (fg_bytes > rows_bytes) rows_bytes = fg_bytes;
+  const size_t smem = sizeof(float) * ((size_t)3 * prm.d * kJointPad) + 16 + sizeof(int2) * (size_t)kBwdWarps * kJointList +
+                      rows_bytes;
   if (smem > 200 * 1024) return BEVPOOL_ERR_BAD_ARG;
   auto kern = pool_bwd_joint_kernel<T>;
   static size_t attr = 0;
