@@ -730,40 +730,33 @@ pool_bwd_block_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
 // ------------------------------------------------------------------------------------------ backward, joint columns
 // Same contract as pool_bwd_block_kernel, for grids where the pixels of one image column mostly land in the
 // same voxel at a given depth bin (Z == 1 BEV grids: the 4 pixels (h0..h0+3, w) of a warp's column differ only
-// in height). The warp walks its 4 pixels JOINTLY: per depth bin the distinct voxel ranks among the 4 pixels
-// become list entries {rank, bin, pixel mask}; one out_grad row is loaded per entry and applied to every pixel
-// in the mask (4 dot products + 4 feat_grad updates per row instead of one load per point). Grids where the
-// ranks differ simply get more entries with single-bit masks — the result is identical either way.
-constexpr int kJointPad = kPixBlock + 1;   // row stride of the staged [d][pixel] arrays (conflict-free by bin)
-constexpr int kJointList = 128;            // list entries per 32-bin round: 4 pixels x 32 bins
+// in height, so they share the voxel or fall out of the z-range). The warp walks its 4 pixels JOINTLY, bin by
+// bin: ONE out_grad row is loaded per bin and applied to every kept pixel (4 dot products + 4 feat_grad
+// updates per row instead of one row load per point). Bins whose kept pixels do NOT share one voxel take a
+// per-pixel slow path, so the result is the same on any grid — only the speed differs.
+//
+// The kernel is issue-bound, so the inner loop is kept minimal: the staged arrays are [d][w] vectors over the
+// 4 rows (one broadcast 128-bit shared load gives all 4 ranks / depths of a bin), there are no lists and no
+// compaction, the channel count is a template constant (CH4 = C/4 active lanes, immediate offsets), and the
+// cross-lane sums of the dot products are done 8 bins at a time by a transposed shared-memory read (each lane
+// parks its 4 partials in a [bin][lane] slot; lane (bin, pixel) then adds the CH4 partials) instead of
+// shuffle trees.
+constexpr int kJointPad = kPixBlock + 1;   // row stride of the [c][pixel] feat_grad transpose tile
+constexpr int kJointBins = 8;              // bins per reduce group
 
-constexpr int kJointRows = 16;   // out_grad rows a warp keeps in flight (cp.async into shared memory)
-
-template <typename T>
-__device__ __forceinline__ void cp_async_chunk(void* smem_dst, const T* gsrc) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  if (sizeof(T) == 4)
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
-  else
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
-}
-
-template <typename T>
+template <typename T, int CH4>
 __global__ void __launch_bounds__(kBwdThreads, 3)
 pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, const T* __restrict__ feat,
                       const int* __restrict__ point_rank, BwdParams prm, T* __restrict__ depth_grad,
                       T* __restrict__ feat_grad) {
-  extern __shared__ unsigned char smem_raw[];
-  int* s_rank = reinterpret_cast<int*>(smem_raw);                                   // [d][33]
-  float* s_depth = reinterpret_cast<float*>(smem_raw) + (size_t)prm.d * kJointPad;   // [d][33]
-  float* s_dg = s_depth + (size_t)prm.d * kJointPad;                                 // [d][33]
-  int2* s_list = reinterpret_cast<int2*>(                                            // [8 warps][128] {rank, bin | mask << 16}
-      (reinterpret_cast<uintptr_t>(s_dg + (size_t)prm.d * kJointPad) + 15) & ~(uintptr_t)15);
-  // [8 warps][16 rows][cw] staged out_grad rows; re-used as the [cw][33] feat_grad transpose tile at the end
-  float* s_rows_f = reinterpret_cast<float*>(s_list + (size_t)kBwdWarps * kJointList);   // row stride: cw floats
-  float* s_fg = s_rows_f;
+  constexpr int C = CH4 * 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int4* s_rank4 = reinterpret_cast<int4*>(smem_raw);                               // [d][8]: ranks of rows h0..h0+3
+  float4* s_depth4 = reinterpret_cast<float4*>(s_rank4 + (size_t)prm.d * kPixW);   // [d][8]: 0 where dropped
+  float4* s_dg4 = s_depth4 + (size_t)prm.d * kPixW;                                // [d][8]
+  float* s_part = reinterpret_cast<float*>(s_dg4 + (size_t)prm.d * kPixW);         // [8 warps][8 bins][C]; later [C][33]
+  float* s_fg = s_part;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
-  const int c4 = prm.c >> 2;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 
   const int blk = blockIdx.x;
@@ -772,7 +765,7 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
   const int brem = blk - bn * per_img;
   const int bh = brem / prm.blocks_w, bw = brem - bh * prm.blocks_w;
   const int h0 = bh * kPixH, w0 = bw * kPixW;
-  const int64_t hw = (int64_t)prm.h * prm.w;
+  const int hw = prm.h * prm.w;
   const int64_t img_base = (int64_t)bn * prm.d * hw;
   unsigned long long t_s = 0, t_a = 0, t_b = 0;
   if (g_fwd_timeline_on && threadIdx.x == 0) t_s = globaltimer_ns();
@@ -780,10 +773,9 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
   // ---- stage point_rank / depth of the block: 8 consecutive w = one 32-byte sector per (d, h);
   //      8 bins per thread are loaded before anything is stored (one memory latency, not eight)
   {
-    const int px = threadIdx.x & 31;
-    const int hh = h0 + (px >> 3), wx = w0 + (px & 7);
-    const bool in = hh < prm.h && wx < prm.w;
-    const int64_t o0 = img_base + (int64_t)hh * prm.w + wx;
+    const int hl = lane >> 3, wl = lane & 7;
+    const bool in = h0 + hl < prm.h && w0 + wl < prm.w;
+    const int64_t o0 = img_base + (h0 + hl) * prm.w + w0 + wl;
     for (int d0 = 0; d0 < prm.d; d0 += 8 * kBwdWarps) {
       int r[8];
       float dv[8];
@@ -793,17 +785,16 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
         r[k] = -1;
         dv[k] = 0.f;
         if (in && dd < prm.d) {
-          r[k] = ldg_stream_i32(point_rank + o0 + dd * hw);
-          dv[k] = Vec4<T>::load1(depth, o0 + dd * hw);
+          r[k] = ldg_stream_i32(point_rank + o0 + (int64_t)dd * hw);
+          dv[k] = Vec4<T>::load1(depth, o0 + (int64_t)dd * hw);
         }
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int dd = d0 + k * kBwdWarps + warp;
         if (dd < prm.d) {
-          s_rank[dd * kJointPad + px] = r[k];
-          s_depth[dd * kJointPad + px] = dv[k];
-          s_dg[dd * kJointPad + px] = 0.f;
+          reinterpret_cast<int*>(s_rank4 + dd * kPixW + wl)[hl] = r[k];
+          reinterpret_cast<float*>(s_depth4 + dd * kPixW + wl)[hl] = r[k] >= 0 ? dv[k] : 0.f;
         }
       }
     }
@@ -811,162 +802,125 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
   __syncthreads();
   if (g_fwd_timeline_on && threadIdx.x == 0) t_a = globaltimer_ns();
 
-  int2* my_list = s_list + (size_t)warp * kJointList;
-  const int ww = w0 + warp;   // this warp's image column; its pixels are px = hl*8 + warp, hl = 0..3
-  for (int cb = 0; cb < c4; cb += 32) {
-    const bool act = cb + lane < c4;
-    const int cw = min(prm.c - 4 * cb, 128);
-    const int lane_c = 4 * (cb + min(lane, c4 - 1 - cb));
-    const T* og_lane = og + lane_c;
-    float* my_rows = s_rows_f + (size_t)warp * kJointRows * cw + 4 * min(lane, c4 - 1 - cb);   // this lane's 16-byte slot
-    float4 fv[kPixH], fg[kPixH];
+  const int ww = w0 + warp;   // this warp's image column
+  const bool act = lane < CH4;
+  const int lane_c = 4 * (act ? lane : CH4 - 1);          // idle lanes alias the last chunk; never stored
+  const T* og_lane = og + lane_c;
+  constexpr int PS = C + 4;   // partial-row stride: (20*k + p + 4*l) mod 32 is conflict-free for the transposed read
+  float* my_part = s_part + (size_t)warp * kJointBins * PS + lane_c;
+  float4 fv[kPixH], fg[kPixH];
 #pragma unroll
-    for (int p = 0; p < kPixH; ++p) {
-      fg[p] = zero;
-      const int hh = h0 + p;
-      fv[p] = (ww < prm.w && hh < prm.h)
-                  ? Vec4<T>::load(feat, ((int64_t)bn * hw + (int64_t)hh * prm.w + ww) * prm.c + lane_c) : zero;
-    }
-    if (ww < prm.w) {   // warp-uniform
-      for (int d0 = 0; d0 < prm.d; d0 += 32) {
-        // ---- entries of up to 32 bins: one lane per bin dedups the ranks of its 4 pixels
-        const int dd = d0 + lane;
-        int r[kPixH];
+  for (int p = 0; p < kPixH; ++p) {
+    fg[p] = zero;
+    fv[p] = (ww < prm.w && h0 + p < prm.h)
+                ? Vec4<T>::load(feat, ((int64_t)bn * hw + (h0 + p) * prm.w + ww) * C + lane_c) : zero;
+  }
+  if (ww < prm.w) {   // warp-uniform
+    const int4* rank_col = s_rank4 + warp;
+    const float4* depth_col = s_depth4 + warp;
+    for (int d0 = 0; d0 < prm.d; d0 += kJointBins) {
 #pragma unroll
-        for (int p = 0; p < kPixH; ++p) r[p] = (dd < prm.d) ? s_rank[dd * kJointPad + p * kPixW + warp] : -1;
-        unsigned todo = 0;
+      for (int k0 = 0; k0 < kJointBins; k0 += 4) {
+        // 4 bins at a time: lead rows requested first, then consumed
+        int4 r[4];
+        int lead[4];
+        float4 g[4];
 #pragma unroll
-        for (int p = 0; p < kPixH; ++p) todo |= (r[p] >= 0) ? (1u << p) : 0u;
-        // unique ranks in pixel order; slot k of this lane = k-th distinct rank
-        int er[kPixH], em[kPixH];
-        int ne = 0;
-#pragma unroll
-        for (int p = 0; p < kPixH; ++p) {
-          er[p] = -1;
-          em[p] = 0;
+        for (int u = 0; u < 4; ++u) {
+          const int dd = d0 + k0 + u;
+          r[u] = dd < prm.d ? rank_col[dd * kPixW] : make_int4(-1, -1, -1, -1);   // broadcast
+          lead[u] = max(max(r[u].x, r[u].y), max(r[u].z, r[u].w));                 // any kept rank (-1: none)
+          g[u] = zero;
+          if (lead[u] >= 0) g[u] = Vec4<T>::load(og_lane, (int64_t)lead[u] * C);
         }
 #pragma unroll
-        for (int p = 0; p < kPixH; ++p) {
-          if (todo & (1u << p)) {
-            unsigned m = 0;
+        for (int u = 0; u < 4; ++u) {
+          if (lead[u] < 0) continue;   // warp-uniform
+          const int dd = d0 + k0 + u;
+          const float4 dp = depth_col[dd * kPixW];
+          const int rr[kPixH] = {r[u].x, r[u].y, r[u].z, r[u].w};
+          const float dw[kPixH] = {dp.x, dp.y, dp.z, dp.w};
+          float dt[kPixH];
+          const bool shared = (rr[0] < 0 || rr[0] == lead[u]) && (rr[1] < 0 || rr[1] == lead[u]) &&
+                              (rr[2] < 0 || rr[2] == lead[u]) && (rr[3] < 0 || rr[3] == lead[u]);
+          if (shared) {   // every kept pixel of the column sits in the lead voxel
 #pragma unroll
-            for (int q = p; q < kPixH; ++q) m |= (((todo >> q) & 1u) && r[q] == r[p]) ? (1u << q) : 0u;
-            todo &= ~m;
-            // write into slot `ne` without dynamic register indexing
-#pragma unroll
-            for (int k = 0; k < kPixH; ++k)
-              if (k == ne) { er[k] = r[p]; em[k] = (int)m; }
-            ++ne;
-          }
-        }
-        int incl = ne;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(kFullMask, incl, o);
-          if (lane >= o) incl += t;
-        }
-        const int n_ent = __shfl_sync(kFullMask, incl, 31);
-        const int base = incl - ne;
-#pragma unroll
-        for (int k = 0; k < kPixH; ++k)
-          if (k < ne) my_list[base + k] = make_int2(er[k], dd | (em[k] << 16));
-        __syncwarp();
-
-        // ---- groups of 16 entries: all their out_grad rows are in flight at once (cp.async), then consumed.
-        //      Each lane overwrites the 16 bytes it consumed with its 4 partial dot products, so the cross-lane
-        //      sums are done afterwards by a transposed read (lane = (entry, pixel)) instead of shuffle trees.
-        const int nact = min(32, c4 - cb);
-        for (int g0 = 0; g0 < n_ent; g0 += kJointRows) {
-          const int ng = min(kJointRows, n_ent - g0);
-          for (int e = 0; e < ng; ++e)
-            cp_async_chunk<T>(reinterpret_cast<T*>(my_rows + (size_t)e * cw), og_lane + (int64_t)my_list[g0 + e].x * prm.c);
-          asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
-          // each lane reads back only the bytes it copied itself: no warp barrier needed here
-#pragma unroll 2
-          for (int e = 0; e < ng; ++e) {
-            const int meta = my_list[g0 + e].y;
-            float* slot = my_rows + (size_t)e * cw;
-            const float4 g = Vec4<T>::load_smem(reinterpret_cast<const T*>(slot));
-            const float* dp = s_depth + (meta & 0xffff) * kJointPad + warp;
-            float4 d4;
-            if ((meta >> 16) == 0xF) {   // warp-uniform, the common case on Z == 1 grids
-              fg[0] = fma4(g, dp[0 * kPixW], fg[0]);
-              fg[1] = fma4(g, dp[1 * kPixW], fg[1]);
-              fg[2] = fma4(g, dp[2 * kPixW], fg[2]);
-              fg[3] = fma4(g, dp[3 * kPixW], fg[3]);
-              d4 = make_float4(dot4_packed(g, fv[0]), dot4_packed(g, fv[1]), dot4_packed(g, fv[2]), dot4_packed(g, fv[3]));
-            } else {
-              float dd[kPixH];
-#pragma unroll
-              for (int p = 0; p < kPixH; ++p) {
-                dd[p] = 0.f;
-                if ((meta >> (16 + p)) & 1) {
-                  fg[p] = fma4(g, dp[p * kPixW], fg[p]);
-                  dd[p] = dot4_packed(g, fv[p]);
-                }
+            for (int p = 0; p < kPixH; ++p) {
+              dt[p] = 0.f;
+              if (rr[p] >= 0) {   // warp-uniform predicate
+                fg[p] = fma4(g[u], dw[p], fg[p]);
+                dt[p] = dot4_packed(g[u], fv[p]);
               }
-              d4 = make_float4(dd[0], dd[1], dd[2], dd[3]);
             }
-            if (act) *reinterpret_cast<float4*>(slot) = d4;
-          }
-          __syncwarp();
-          // value v = (entry, pixel): sum the partials of the active lanes, write depth_grad's staging slot
-          for (int v = lane; v < 4 * ng; v += 32) {
-            const int e = v >> 2, pz = v & 3;
-            const int meta = my_list[g0 + e].y;
-            if ((meta >> (16 + pz)) & 1) {
-              const float* src = s_rows_f + ((size_t)warp * kJointRows + e) * cw + pz;
-              float sum = 0.f;
-              for (int l = 0; l < nact; ++l) sum += src[4 * l];
-              float* out_slot = s_dg + (meta & 0xffff) * kJointPad + pz * kPixW + warp;
-              *out_slot = (cb == 0) ? sum : *out_slot + sum;
-            }
-          }
-          __syncwarp();
-        }
-        __syncwarp();
-      }
-    }
-    // ---- feat_grad of the 4 pixels
-    if (prm.feat_grad_nchw) __syncthreads();   // every warp is done with its row buffer: re-use it as s_fg
+          } else {
 #pragma unroll
-    for (int p = 0; p < kPixH; ++p) {
-      const int hh = h0 + p;
-      if (ww >= prm.w || hh >= prm.h) continue;
-      if (prm.feat_grad_nchw) {
-        if (act) {
-          float* c = s_fg + (4 * lane) * kJointPad + p * kPixW + warp;
-          c[0 * kJointPad] = fg[p].x;
-          c[1 * kJointPad] = fg[p].y;
-          c[2 * kJointPad] = fg[p].z;
-          c[3 * kJointPad] = fg[p].w;
+            for (int p = 0; p < kPixH; ++p) {
+              dt[p] = 0.f;
+              if (rr[p] >= 0) {
+                const float4 gp = rr[p] == lead[u] ? g[u] : Vec4<T>::load(og_lane, (int64_t)rr[p] * C);
+                fg[p] = fma4(gp, dw[p], fg[p]);
+                dt[p] = dot4_packed(gp, fv[p]);
+              }
+            }
+          }
+          if (act) *reinterpret_cast<float4*>(my_part + (k0 + u) * PS) = make_float4(dt[0], dt[1], dt[2], dt[3]);
         }
-      } else if (act) {
-        Vec4<T>::store(feat_grad, ((int64_t)bn * hw + (int64_t)hh * prm.w + ww) * prm.c + lane_c, fg[p]);
+      }
+      __syncwarp();
+      // ---- lane (k, p) sums the CH4 partial dot products of bin d0 + k, pixel p
+      {
+        const int k = lane >> 2, pz = lane & 3;
+        const int dd = d0 + k;
+        if (dd < prm.d) {
+          const int mine = reinterpret_cast<const int*>(rank_col + dd * kPixW)[pz];
+          float sum = 0.f;
+          if (mine >= 0) {
+            const float* src = s_part + (size_t)warp * kJointBins * PS + k * PS + pz;
+#pragma unroll
+            for (int l = 0; l < CH4; ++l) sum += src[4 * l];
+          }
+          reinterpret_cast<float*>(s_dg4 + dd * kPixW + warp)[pz] = sum;
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    for (int d = lane; d < prm.d; d += 32) s_dg4[d * kPixW + warp] = zero;
+  }
+  // ---- feat_grad of the 4 pixels
+  if (prm.feat_grad_nchw) {
+    __syncthreads();   // every warp is done with its partial buffer: re-use it as the transpose tile
+    if (ww < prm.w && act) {
+#pragma unroll
+      for (int p = 0; p < kPixH; ++p) {
+        float* c = s_fg + lane_c * kJointPad + p * kPixW + warp;
+        c[0 * kJointPad] = fg[p].x;
+        c[1 * kJointPad] = fg[p].y;
+        c[2 * kJointPad] = fg[p].z;
+        c[3 * kJointPad] = fg[p].w;
       }
     }
-    if (prm.feat_grad_nchw) {
-      __syncthreads();
-      const int px = threadIdx.x & 31;
-      const int hh = h0 + (px >> 3), wx = w0 + (px & 7);
-      if (hh < prm.h && wx < prm.w) {
-        const int64_t o0 = ((int64_t)bn * prm.c + 4 * cb) * hw + (int64_t)hh * prm.w + wx;
-        for (int cc = threadIdx.x >> 5; cc < cw; cc += kBwdWarps)
-          Vec4<T>::store1s(feat_grad, o0 + cc * hw, s_fg[cc * kJointPad + px]);
-      }
-      __syncthreads();
+    __syncthreads();
+    const int hl = lane >> 3, wl = lane & 7;
+    if (h0 + hl < prm.h && w0 + wl < prm.w) {
+      const int64_t o0 = (int64_t)bn * C * hw + (h0 + hl) * prm.w + w0 + wl;
+      for (int cc = warp; cc < C; cc += kBwdWarps)
+        Vec4<T>::store1s(feat_grad, o0 + (int64_t)cc * hw, s_fg[cc * kJointPad + lane]);
     }
+  } else if (ww < prm.w && act) {
+#pragma unroll
+    for (int p = 0; p < kPixH; ++p)
+      if (h0 + p < prm.h) Vec4<T>::store(feat_grad, ((int64_t)bn * hw + (h0 + p) * prm.w + ww) * C + lane_c, fg[p]);
   }
   __syncthreads();
   if (g_fwd_timeline_on && threadIdx.x == 0) t_b = globaltimer_ns();
   // ---- depth_grad of the block, zeros for dropped points included
   {
-    const int px = threadIdx.x & 31;
-    const int hh = h0 + (px >> 3), wx = w0 + (px & 7);
-    if (hh < prm.h && wx < prm.w) {
-      const int64_t o0 = img_base + (int64_t)hh * prm.w + wx;
-      for (int dd = threadIdx.x >> 5; dd < prm.d; dd += kBwdWarps)
-        Vec4<T>::store1s(depth_grad, o0 + dd * hw, s_dg[dd * kJointPad + px]);
+    const int hl = lane >> 3, wl = lane & 7;
+    if (h0 + hl < prm.h && w0 + wl < prm.w) {
+      const int64_t o0 = img_base + (h0 + hl) * prm.w + w0 + wl;
+      for (int dd = warp; dd < prm.d; dd += kBwdWarps)
+        Vec4<T>::store1s(depth_grad, o0 + (int64_t)dd * hw, reinterpret_cast<const float*>(s_dg4 + dd * kPixW + wl)[hl]);
     }
   }
   if (g_fwd_timeline_on && threadIdx.x == 0 && blk < 8192) {
@@ -1074,22 +1028,16 @@ static int forward_stream_t(const void* depth, const void* feat, void* out, cons
   return launch_status();
 }
 
-template <typename T>
-static int backward_joint_t(const void* og, void* dg, void* fg, const void* depth, const void* feat,
-                            const int* point_rank, BwdParams prm, cudaStream_t st) {
-  prm.blocks_w = (prm.w + kPixW - 1) / kPixW;
-  prm.blocks_h = (prm.h + kPixH - 1) / kPixH;
-  const int64_t n_blocks = (int64_t)prm.bn * prm.blocks_w * prm.blocks_h;
-  if (n_blocks == 0) return 0;
-  if (n_blocks > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
-  const int cw = prm.c < 128 ? prm.c : 128;
-  size_t rows_bytes = sizeof(float) * (size_t)kBwdWarps * kJointRows * cw;
-  const size_t fg_bytes = prm.feat_grad_nchw ? sizeof(float) * (size_t)cw * kJointPad : 0;
-  if (fg_bytes > rows_bytes) rows_bytes = fg_bytes;
-  const size_t smem = sizeof(float) * ((size_t)3 * prm.d * kJointPad) + 16 + sizeof(int2) * (size_t)kBwdWarps * kJointList +
-                      rows_bytes;
+template <typename T, int CH4>
+static int backward_joint_launch(const void* og, void* dg, void* fg, const void* depth, const void* feat,
+                                 const int* point_rank, const BwdParams& prm, int64_t n_blocks, cudaStream_t st) {
+  constexpr int C = CH4 * 4;
+  size_t part_bytes = sizeof(float) * (size_t)kBwdWarps * kJointBins * (C + 4);
+  const size_t fg_bytes = prm.feat_grad_nchw ? sizeof(float) * (size_t)C * kJointPad : 0;
+  if (fg_bytes > part_bytes) part_bytes = fg_bytes;
+  const size_t smem = (size_t)3 * prm.d * kPixW * 16 + part_bytes;
   if (smem > 200 * 1024) return BEVPOOL_ERR_BAD_ARG;
-  auto kern = pool_bwd_joint_kernel<T>;
+  auto kern = pool_bwd_joint_kernel<T, CH4>;
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1099,6 +1047,27 @@ static int backward_joint_t(const void* og, void* dg, void* fg, const void* dept
                                                        (T*)dg, (T*)fg);
   count_launch();
   return launch_status();
+}
+
+// Channel counts with a specialised joint kernel (CH4 = C/4 <= 32). Others use the generic block kernel.
+template <typename T>
+static int backward_joint_t(const void* og, void* dg, void* fg, const void* depth, const void* feat,
+                            const int* point_rank, BwdParams prm, cudaStream_t st, bool* handled) {
+  prm.blocks_w = (prm.w + kPixW - 1) / kPixW;
+  prm.blocks_h = (prm.h + kPixH - 1) / kPixH;
+  const int64_t n_blocks = (int64_t)prm.bn * prm.blocks_w * prm.blocks_h;
+  *handled = true;
+  if (n_blocks == 0) return 0;
+  if (n_blocks > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
+  switch (prm.c) {
+    case 32: return backward_joint_launch<T, 8>(og, dg, fg, depth, feat, point_rank, prm, n_blocks, st);
+    case 64: return backward_joint_launch<T, 16>(og, dg, fg, depth, feat, point_rank, prm, n_blocks, st);
+    case 80: return backward_joint_launch<T, 20>(og, dg, fg, depth, feat, point_rank, prm, n_blocks, st);
+    case 128: return backward_joint_launch<T, 32>(og, dg, fg, depth, feat, point_rank, prm, n_blocks, st);
+    default: break;
+  }
+  *handled = false;
+  return 0;
 }
 
 template <typename T>
@@ -1233,13 +1202,19 @@ extern "C" int bevpool_v2_backward_dense(const void* out_grad, void* depth_grad,
   prm.feat_grad_nchw = feat_grad_nchw ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (d >= 65536) return BEVPOOL_ERR_BAD_ARG;
+  if (dtype != BEVPOOL_F32 && dtype != BEVPOOL_BF16) return BEVPOOL_ERR_BAD_ARG;
+  if (column_hint) {
+    bool handled = false;
+    const int rc = dtype == BEVPOOL_F32
+                       ? backward_joint_t<float>(out_grad, depth_grad, feat_grad, depth, feat, point_rank, prm, st, &handled)
+                       : backward_joint_t<__nv_bfloat16>(out_grad, depth_grad, feat_grad, depth, feat, point_rank, prm, st,
+                                                         &handled);
+    if (handled) return rc;
+  }
   if (dtype == BEVPOOL_F32)
-    return column_hint ? backward_joint_t<float>(out_grad, depth_grad, feat_grad, depth, feat, point_rank, prm, st)
-                       : backward_block_t<float>(out_grad, depth_grad, feat_grad, depth, feat, point_rank, prm, st);
+    return backward_block_t<float>(out_grad, depth_grad, feat_grad, depth, feat, point_rank, prm, st);
   if (dtype == BEVPOOL_BF16)
-    return column_hint
-               ? backward_joint_t<__nv_bfloat16>(out_grad, depth_grad, feat_grad, depth, feat, point_rank, prm, st)
-               : backward_block_t<__nv_bfloat16>(out_grad, depth_grad, feat_grad, depth, feat, point_rank, prm, st);
+    return backward_block_t<__nv_bfloat16>(out_grad, depth_grad, feat_grad, depth, feat, point_rank, prm, st);
   return BEVPOOL_ERR_BAD_ARG;
 }
 
