@@ -745,7 +745,7 @@ constexpr int kJointPad = kPixBlock + 1;   // row stride of the [c][pixel] feat_
 constexpr int kJointBins = 8;              // bins per reduce group
 
 template <typename T, int CH4>
-__global__ void __launch_bounds__(kBwdThreads, 3)
+__global__ void __launch_bounds__(kBwdThreads, 2)
 pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, const T* __restrict__ feat,
                       const int* __restrict__ point_rank, BwdParams prm, T* __restrict__ depth_grad,
                       T* __restrict__ feat_grad) {
