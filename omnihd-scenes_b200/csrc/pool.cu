@@ -314,6 +314,11 @@ static int transpose_cl_t(const void* src, void* dst, int b, int c, int64_t cols
   if (total == 0) return 0;
   if (total > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
   const size_t smem = sizeof(float) * (size_t)c * (kTcCols + 1);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaFuncSetAttribute(transpose_to_channels_last_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
   transpose_to_channels_last_kernel<T><<<(unsigned)total, 256, smem, st>>>((const T*)src, (T*)dst, c, cols, tiles_per_batch);
   count_launch();
   return launch_status();

@@ -93,6 +93,7 @@ __device__ __forceinline__ void load_point(const T* __restrict__ depth, const in
     const int rem = rd_val - cam * prm.dhw;                                                // d*HW + hw
     f = cam * prm.hw + rem % prm.hw;
   }
+  f = (int)((unsigned)f * (unsigned)prm.c);   // element offset of the feature row as u32 (F*C < 2^32 elements)
   d = Vec4<T>::load1(depth, rd_val);
   col = ldg_stream_i32(rb + p) - rank_col0;
 }
@@ -163,7 +164,7 @@ __device__ __forceinline__ void chunk_sum(const T* __restrict__ depth, const T* 
         float4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          v[u] = Vec4<T>::load(feat_lane, (int64_t)__shfl_sync(kFullMask, my_f, i0 + u) * prm.c);
+          v[u] = Vec4<T>::load(feat_lane, (unsigned)__shfl_sync(kFullMask, my_f, i0 + u));
         const unsigned m8 = bmask >> i0;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -182,7 +183,7 @@ __device__ __forceinline__ void chunk_sum(const T* __restrict__ depth, const T* 
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int f = __shfl_sync(kFullMask, my_f, i0 + u);
-          v[u] = (i0 + u < n) ? Vec4<T>::load(feat_lane, (int64_t)f * prm.c) : zero;
+          v[u] = (i0 + u < n) ? Vec4<T>::load(feat_lane, (unsigned)f) : zero;
         }
         const unsigned m8 = bmask >> i0;
 #pragma unroll
@@ -421,7 +422,7 @@ __device__ __forceinline__ void chunk_stream(const T* __restrict__ depth, const 
         float4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          v[u] = Vec4<T>::load(feat_lane, (int64_t)__shfl_sync(kFullMask, my_f, i0 + u) * prm.c);
+          v[u] = Vec4<T>::load(feat_lane, (unsigned)__shfl_sync(kFullMask, my_f, i0 + u));
         const unsigned m8 = (bmask >> i0) & 0xffu;
         if (m8 == 0) {   // common: the 8 points stay inside the current voxel
 #pragma unroll
@@ -445,7 +446,7 @@ __device__ __forceinline__ void chunk_stream(const T* __restrict__ depth, const 
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int f = __shfl_sync(kFullMask, my_f, i0 + u);
-          v[u] = (i0 + u < n) ? Vec4<T>::load(feat_lane, (int64_t)f * prm.c) : zero;
+          v[u] = (i0 + u < n) ? Vec4<T>::load(feat_lane, (unsigned)f) : zero;
         }
         const unsigned m8 = bmask >> i0;
 #pragma unroll
