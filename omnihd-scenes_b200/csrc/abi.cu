@@ -1,11 +1,20 @@
 // Library-level entry points: ABI version, error text, launch counter.
 #include <atomic>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace bevpool {
 static std::atomic<int64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BEVPOOL_PDL");
+    v = !(e && e[0] == '0');
+  }
+  return v != 0;
+}
 }  // namespace bevpool
 
 extern "C" int bevpool_b200_abi_version(void) { return BEVPOOL_B200_ABI_VERSION; }

@@ -24,6 +24,35 @@ inline int launch_status() {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// The kernels of one step form a dependent chain of short launches; with the programmatic-stream-
+// serialization attribute the next grid is set up and its CTAs are dispatched while the previous grid
+// drains, and every kernel blocks at pdl_wait() before it touches global memory (a no-op for a kernel
+// launched the ordinary way). Captured into CUDA graphs as programmatic dependency edges.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // let the NEXT grid be set up as soon as every CTA of this one has got this far: its CTAs take the slots
+  // this grid frees and park at their own pdl_wait() until this grid has completed and flushed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+bool pdl_enabled();   // abi.cu (BEVPOOL_PDL=0 disables)
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- cache-hinted memory ops ---------------------------------------------------------------
 // Streaming (read-once) data: do not allocate in L1 so gathered feature rows keep it.
 __device__ __forceinline__ int ldg_stream_i32(const int* p) {

@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(256)
 transpose_to_channels_last_kernel(const T* __restrict__ src, T* __restrict__ dst, int c, int64_t cols,
                                   int64_t tiles_per_batch) {
   extern __shared__ float t[];   // [c][kTcCols + 1]
+  pdl_wait();
   const int64_t b = blockIdx.x / tiles_per_batch;
   const int64_t col0 = (blockIdx.x % tiles_per_batch) * kTcCols;
   const int ncol = (int)min((int64_t)kTcCols, cols - col0);
@@ -319,7 +320,8 @@ static int transpose_cl_t(const void* src, void* dst, int b, int c, int64_t cols
     cudaFuncSetAttribute(transpose_to_channels_last_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = smem;
   }
-  transpose_to_channels_last_kernel<T><<<(unsigned)total, 256, smem, st>>>((const T*)src, (T*)dst, c, cols, tiles_per_batch);
+  launch_pdl(transpose_to_channels_last_kernel<T>, dim3((unsigned)total), dim3(256), smem, st, (const T*)src, (T*)dst, c, cols,
+             tiles_per_batch);
   count_launch();
   return launch_status();
 }

@@ -31,6 +31,7 @@ namespace bevpool {
 __global__ void __launch_bounds__(256)
 voxel_table_kernel(const int* __restrict__ keys, int64_t n_points, const int* __restrict__ counts_dev,
                    int64_t n_voxels_total, int* __restrict__ vox_pt) {
+  pdl_wait();
   if (counts_dev) n_points = counts_dev[0];
   const int lane = lane_id();
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -473,6 +474,7 @@ pool_fwd_chunk_kernel(const T* __restrict__ depth, const T* __restrict__ feat, T
                       float* __restrict__ part /*[chunks][2][c]*/, int* __restrict__ part_rank /*[chunks][2]*/) {
   const int lane = lane_id();
   const int c4 = prm.c >> 2;
+  pdl_wait();
   if (counts_dev) n_points = counts_dev[0];
   const int64_t cidx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t p64 = cidx * chunk;
@@ -494,6 +496,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 chunk_fixup_kernel(const float* __restrict__ part, const int* __restrict__ part_rank, const int* __restrict__ counts_dev,
                    int n_points, int chunk, int c, T* __restrict__ out_cl) {
+  pdl_wait();
   if (counts_dev) n_points = counts_dev[0];
   const int64_t n_chunks = ((int64_t)n_points + chunk - 1) / chunk;
   const int lane = lane_id();
@@ -520,6 +523,7 @@ cl_to_bczyx_zero_fill_kernel(const T* __restrict__ src_cl, const int* __restrict
                              int c, int64_t vpf, int64_t tiles_per_frame) {
   extern __shared__ float t[];            // [c][kTcCols + 1]
   __shared__ int s_pt[kTcCols + 1];
+  pdl_wait();
   const int64_t b = blockIdx.x / tiles_per_frame;
   const int64_t v0 = (blockIdx.x % tiles_per_frame) * kTcCols;
   const int ncol = (int)min((int64_t)kTcCols, vpf - v0);
@@ -769,6 +773,7 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
   const int hw = prm.h * prm.w;
   const int64_t img_base = (int64_t)bn * prm.d * hw;
   unsigned long long t_s = 0, t_a = 0, t_b = 0;
+  pdl_wait();
   if (g_fwd_timeline_on && threadIdx.x == 0) t_s = globaltimer_ns();
 
   // ---- stage point_rank / depth of the block: 8 consecutive w = one 32-byte sector per (d, h);
@@ -1000,12 +1005,13 @@ static int forward_stream_t(const void* depth, const void* feat, void* out, cons
     if (n_chunks > 0) {
       const unsigned blocks = (unsigned)((n_chunks + 7) / 8);
       if (minb_env >= 4)
-        pool_fwd_chunk_kernel<T, 4><<<blocks, 256, 0, st>>>((const T*)depth, (const T*)feat, rows_dst0, rd, rf, rb, counts_dev,
-                                                             (int)n_points_upper, chunk_env, prm, part, part_rank);
+        launch_pdl(pool_fwd_chunk_kernel<T, 4>, dim3(blocks), dim3(256), 0, st, (const T*)depth, (const T*)feat, rows_dst0, rd, rf,
+                   rb, counts_dev, (int)n_points_upper, chunk_env, prm, part, part_rank);
       else
-        pool_fwd_chunk_kernel<T, 3><<<blocks, 256, 0, st>>>((const T*)depth, (const T*)feat, rows_dst0, rd, rf, rb, counts_dev,
-                                                             (int)n_points_upper, chunk_env, prm, part, part_rank);
-      chunk_fixup_kernel<T><<<blocks, 256, 0, st>>>(part, part_rank, counts_dev, (int)n_points_upper, chunk_env, prm.c, rows_dst0);
+        launch_pdl(pool_fwd_chunk_kernel<T, 3>, dim3(blocks), dim3(256), 0, st, (const T*)depth, (const T*)feat, rows_dst0, rd, rf,
+                   rb, counts_dev, (int)n_points_upper, chunk_env, prm, part, part_rank);
+      launch_pdl(chunk_fixup_kernel<T>, dim3(blocks), dim3(256), 0, st, (const float*)part, (const int*)part_rank, counts_dev,
+                 (int)n_points_upper, chunk_env, prm.c, rows_dst0);
       count_launch(2);
     }
   }
@@ -1018,8 +1024,8 @@ static int forward_stream_t(const void* depth, const void* feat, void* out, cons
       cudaFuncSetAttribute(cl_to_bczyx_zero_fill_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
       attr2 = smem2;
     }
-    cl_to_bczyx_zero_fill_kernel<T><<<(unsigned)(tpf * prm.frames), 256, smem2, st>>>((const T*)scratch, vox_pt, (T*)out,
-                                                                                      prm.c, vpf, tpf);
+    launch_pdl(cl_to_bczyx_zero_fill_kernel<T>, dim3((unsigned)(tpf * prm.frames)), dim3(256), smem2, st, (const T*)scratch,
+               vox_pt, (T*)out, prm.c, vpf, tpf);
   } else {
     int64_t blocks = (n_vox * (prm.c >> 2) + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
@@ -1044,8 +1050,8 @@ static int backward_joint_launch(const void* og, void* dg, void* fg, const void*
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = smem;
   }
-  kern<<<(unsigned)n_blocks, kBwdThreads, smem, st>>>((const T*)og, (const T*)depth, (const T*)feat, point_rank, prm,
-                                                       (T*)dg, (T*)fg);
+  launch_pdl(kern, dim3((unsigned)n_blocks), dim3(kBwdThreads), smem, st, (const T*)og, (const T*)depth, (const T*)feat,
+             point_rank, prm, (T*)dg, (T*)fg);
   count_launch();
   return launch_status();
 }
@@ -1106,8 +1112,8 @@ extern "C" int bevpool_voxel_table(const int32_t* ranks_bev_sorted, int64_t n_po
   int64_t blocks = (n_points + 1 + 255) / 256;   // n_points is an upper bound when the count lives on the device
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   if (blocks < 1) blocks = 1;
-  voxel_table_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ranks_bev_sorted, n_points, counts_dev,
-                                                                        n_voxels_total, vox_pt);
+  launch_pdl(voxel_table_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const int*)ranks_bev_sorted,
+             n_points, (const int*)counts_dev, n_voxels_total, (int*)vox_pt);
   count_launch();
   return launch_status();
 }

@@ -250,6 +250,7 @@ key_hist_kernel(const int* __restrict__ keys, int64_t n, SortPlan plan, uint32_t
 __global__ void __launch_bounds__(256)
 tile_scan_kernel(uint32_t* __restrict__ hist, int64_t n_tiles, int bins) {
   __shared__ uint32_t scan_tmp[8];
+  pdl_wait();
   const int d = blockIdx.x;
   uint32_t carry = 0;
   for (int64_t t0 = 0; t0 < n_tiles; t0 += 256) {
@@ -279,6 +280,7 @@ radix_scatter_kernel(const int* __restrict__ keys_in, const int* __restrict__ va
   __shared__ uint32_t scan_tmp[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bins = 1 << bits;
+  pdl_wait();
   const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
   const int64_t tile_keys = (int64_t)rounds * kSortRound;
   const int64_t tile_base = (int64_t)blockIdx.x * tile_keys;
@@ -534,11 +536,11 @@ static void run_passes(const SortPlan& plan, const SortWorkspace& w, const int* 
       next = (p + 1 == 2) ? w.hist_even2 : w.hist_odd;
       if (p + 1 == 3) cudaMemsetAsync(w.hist_odd, 0, sizeof(uint32_t) * (size_t)plan.n_tiles * kMaxBins, st);
     }
-    tile_scan_kernel<<<bins, 256, 0, st>>>(hist, plan.n_tiles, bins);
+    launch_pdl(tile_scan_kernel, dim3(bins), dim3(256), 0, st, hist, plan.n_tiles, bins);
     count_launch();
-    radix_scatter_kernel<<<(unsigned)plan.n_tiles, kSortThreads, 0, st>>>(
-        src_k, src_v, dst_k, dst_v, w.totals + p * kMaxBins, hist, next, p == 0 ? nullptr : n_dev, n0, plan.shift[p],
-        plan.bits[p], plan.rounds, next ? plan.shift[p + 1] : 0, next ? plan.bits[p + 1] : 1);
+    launch_pdl(radix_scatter_kernel, dim3((unsigned)plan.n_tiles), dim3(kSortThreads), 0, st, src_k, src_v, dst_k, dst_v,
+               (const uint32_t*)(w.totals + p * kMaxBins), (const uint32_t*)hist, next, p == 0 ? (const int*)nullptr : n_dev,
+               n0, plan.shift[p], plan.bits[p], plan.rounds, next ? plan.shift[p + 1] : 0, next ? plan.bits[p + 1] : 1);
     count_launch();
     src_k = dst_k;
     src_v = dst_v;
