@@ -166,7 +166,8 @@ def run_native_arm(args):
     cfg = pkg.synthetic.CONFIGS[args.config]
     B = cfg.batch if args.frames is None else args.frames     # frames per GPU (weak scaling)
     dt_t = torch.bfloat16 if cfg.dtype == "bf16" else torch.float32
-    view = pkg.LSSViewTransform.from_config(cfg).to(dev)
+    groups = args.frame_groups if B % max(args.frame_groups, 1) == 0 else 1
+    view = pkg.LSSViewTransform.from_config(cfg, frame_groups=groups).to(dev)
     X, Y, Z = (int(v) for v in view.nx)
     C, D, H, W, N = cfg.channels, view.D, view.fH, view.fW, cfg.n_cams
     V, F, P0 = B * X * Y * Z, B * N * H * W, B * N * D * H * W
@@ -428,6 +429,7 @@ def run_native_arm(args):
         "config": {"workload": args.config, "frames_per_gpu": B, "cams": N, "feat": [H, W], "D": D, "C": C,
                    "grid": [X, Y, Z], "P0": P0, "P": P, "I": I,
                    "step": "geometry+prepare+fwd+bwd (public API, one CUDA graph per buffer set)",
+                   "frame_groups": groups,
                    "l2": f"inputs rotated over {N_BUFFER_SETS} buffer sets (> 126 MB L2 in total), no explicit flush",
                    "parallelism": f"frame-sharded x{world}, no collective on the path"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -462,6 +464,8 @@ def main():
     ap.add_argument("--config", default=WORKLOAD)
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU (default: the config's batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frame-groups", type=int, default=4,
+                    help="independent frame groups run on concurrent streams inside one step (1 = single stream)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -155,46 +155,97 @@ def voxel_pooling_prepare_v2(coor, dx, bx, nx):
 
 
 # ----------------------------------------------------------------------------- fused module path
+_SIDE_STREAMS = {}
+
+
+def _side_streams(device, n):
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    pool = _SIDE_STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
+class _Fork:
+    """Run frame groups on side streams that fork from / join into the current stream. Frames are
+    independent, so the groups' kernels overlap and fill each other's tails and launch gaps; with one
+    group nothing is forked. Works under CUDA-graph capture (parallel graph branches)."""
+
+    def __init__(self, device, groups):
+        self.cur = torch.cuda.current_stream(device)
+        self.streams = _side_streams(device, groups) if groups > 1 else [self.cur]
+        if groups > 1:
+            for st in self.streams:
+                st.wait_stream(self.cur)
+
+    def join(self):
+        if len(self.streams) > 1 or self.streams[0] is not self.cur:
+            for st in self.streams:
+                self.cur.wait_stream(st)
+
+
 class _FusedViewPool(torch.autograd.Function):
     """geometry -> rank -> sort -> pool with no host synchronisation: point counts stay on the device
     (counts_dev), buffers are worst-case sized. Takes feat as the neck produces it ([B,N,C,H,W]); the
     NCHW->NHWC transpose (reference :282), the zero fill, the pooling and the output permute are our
-    kernels, and the backward is the sort-free kernel writing feat_grad straight back in [B,N,C,H,W]."""
+    kernels, and the backward is the sort-free kernel writing feat_grad straight back in [B,N,C,H,W].
+    The frame batch is cut into `groups` independent groups that run on concurrent streams."""
 
     @staticmethod
-    def forward(ctx, depth, feat, prepared, shape):
-        B, Z, Y, X, C = shape
-        pr = prepared
+    def forward(ctx, depth, feat, rots, trans, view, groups):
+        B, N = trans.shape[:2]
+        D, H, W = view.D, view.fH, view.fW
+        C = feat.shape[2]
+        X, Y, Z = (int(v) for v in view.nx)
         depth = depth.contiguous()
         feat = feat.contiguous()
         if depth.dtype != feat.dtype or depth.dtype not in (torch.float32, torch.bfloat16):
             depth, feat = depth.float(), feat.float()
-        feat_cl = feat.new_empty((pr.bn, pr.h, pr.w, C))
-        _launch_transpose(feat, feat_cl, pr.bn, C, pr.hw, True)           # [BN,C,HW] -> [BN,HW,C]
-        vox_pt = _launch_voxel_table(pr.rb, pr.p0, pr.counts, B * Z * Y * X)
+        rots, trans = rots.contiguous(), trans.contiguous()
         out = feat.new_empty((B, C, Z, Y, X))
-        _launch_forward_dense(depth, feat_cl, out, pr.rd, None, pr.rb, vox_pt, B, Z * Y, X, _lib.LAYOUT_BCZYX,
-                              dhw=pr.d * pr.hw, hw=pr.hw, n_points=pr.p0, counts_dev=pr.counts)
-        ctx.prepared, ctx.shape, ctx.feat_shape = pr, shape, feat.shape
-        ctx.save_for_backward(depth, feat_cl)
+        n = B // groups
+        saved = []
+        fork = _Fork(feat.device, groups)
+        for g, st in enumerate(fork.streams):
+            sl = slice(g * n, (g + 1) * n)
+            with torch.cuda.stream(st):
+                pr = _prepare_device(None, view.frustum, rots[sl], trans[sl], n, N, D, H, W, view.dx, view.bx, view.nx,
+                                     feat.device, want_intervals=False)
+                feat_cl = feat.new_empty((pr.bn, H, W, C))
+                _launch_transpose(feat[sl], feat_cl, pr.bn, C, pr.hw, True)           # [BN,C,HW] -> [BN,HW,C]
+                vox_pt = _launch_voxel_table(pr.rb, pr.p0, pr.counts, n * Z * Y * X)
+                _launch_forward_dense(depth[sl], feat_cl, out[sl], pr.rd, None, pr.rb, vox_pt, n, Z * Y, X,
+                                      _lib.LAYOUT_BCZYX, dhw=D * pr.hw, hw=pr.hw, n_points=pr.p0, counts_dev=pr.counts)
+            saved.append((pr, feat_cl))
+        fork.join()
+        ctx.saved, ctx.dims, ctx.groups = saved, (B, N, C, D, H, W, X, Y, Z), groups
+        ctx.save_for_backward(depth)
         return out
 
     @staticmethod
     def backward(ctx, out_grad):
-        depth, feat_cl = ctx.saved_tensors
-        B, Z, Y, X, C = ctx.shape
-        pr = ctx.prepared
-        out_grad = out_grad.contiguous().to(feat_cl.dtype)
-        og_cl = out_grad.new_empty((B, Z, Y, X, C))
-        _launch_transpose(out_grad, og_cl, B, C, Z * Y * X, True)
+        (depth,) = ctx.saved_tensors
+        B, N, C, D, H, W, X, Y, Z = ctx.dims
+        groups = ctx.groups
+        n = B // groups
+        dt = ctx.saved[0][1].dtype
+        out_grad = out_grad.contiguous().to(dt)
         depth_grad = torch.empty_like(depth)
-        feat_grad = feat_cl.new_empty(ctx.feat_shape)                     # [B,N,C,H,W]
+        feat_grad = depth.new_empty((B, N, C, H, W))
         lib = _lib.load()
-        _lib.check(lib.bevpool_v2_backward_dense(_ptr(og_cl), _ptr(depth_grad), _ptr(feat_grad), _ptr(depth),
-                                                 _ptr(feat_cl), _ptr(pr.point_rank), pr.bn, pr.d, pr.h, pr.w, C, 1,
-                                                 1 if Z == 1 else 0, _dtype_code(feat_cl), _stream()),
-                   "bevpool_v2_backward_dense")
-        return depth_grad, feat_grad, None, None
+        fork = _Fork(depth.device, groups)
+        for g, st in enumerate(fork.streams):
+            sl = slice(g * n, (g + 1) * n)
+            pr, feat_cl = ctx.saved[g]
+            with torch.cuda.stream(st):
+                og_cl = out_grad.new_empty((n, Z, Y, X, C))
+                _launch_transpose(out_grad[sl], og_cl, n, C, Z * Y * X, True)
+                _lib.check(lib.bevpool_v2_backward_dense(_ptr(og_cl), _ptr(depth_grad[sl]), _ptr(feat_grad[sl]),
+                                                         _ptr(depth[sl]), _ptr(feat_cl), _ptr(pr.point_rank), pr.bn, D, H,
+                                                         W, C, 1, 1 if Z == 1 else 0, _dtype_code(feat_cl), _stream()),
+                           "bevpool_v2_backward_dense")
+        fork.join()
+        return depth_grad, feat_grad, None, None, None, None
 
 
 class LSSViewTransform(nn.Module):
@@ -202,8 +253,9 @@ class LSSViewTransform(nn.Module):
     same attribute names (`dx`, `bx`, `nx`, `frustum`, `D`, `fH`, `fW`) and method names, no conv nets.
     Per-axis bounds are accepted (the reference forces one scalar `grid` for x, y and z, :164-169)."""
 
-    def __init__(self, final_dim, downsample, dbound, xbound, ybound, zbound):
+    def __init__(self, final_dim, downsample, dbound, xbound, ybound, zbound, frame_groups=1):
         super().__init__()
+        self.frame_groups = frame_groups          # fused path: independent frame groups on concurrent streams
         self.final_dim = tuple(final_dim)
         self.downsample = downsample
         self.grid_conf = dict(xbound=list(xbound), ybound=list(ybound), zbound=list(zbound), dbound=list(dbound))
@@ -213,8 +265,8 @@ class LSSViewTransform(nn.Module):
         self.D = self.frustum.shape[0]
 
     @classmethod
-    def from_config(cls, cfg):
-        return cls(cfg.final_dim, cfg.downsample, cfg.dbound, cfg.xbound, cfg.ybound, cfg.zbound)
+    def from_config(cls, cfg, frame_groups=1):
+        return cls(cfg.final_dim, cfg.downsample, cfg.dbound, cfg.xbound, cfg.ybound, cfg.zbound, frame_groups)
 
     @classmethod
     def from_lss_args(cls, final_dim, camera_depth_range, pc_range, downsample, grid):
@@ -266,7 +318,5 @@ class LSSViewTransform(nn.Module):
         C = feat.shape[2]
         if C % 4:
             raise ValueError("the fused path needs C % 4 == 0; use voxel_pooling_v2 for other channel counts")
-        pr = _prepare_device(None, self.frustum, rots.contiguous(), trans.contiguous(), B, N, D, H, W,
-                             self.dx, self.bx, self.nx, rots.device, want_intervals=False)
-        shape = (B, int(self.nx[2]), int(self.nx[1]), int(self.nx[0]), C)
-        return _FusedViewPool.apply(depth, feat, pr, shape)
+        groups = self.frame_groups if (self.frame_groups > 1 and B % self.frame_groups == 0) else 1
+        return _FusedViewPool.apply(depth, feat, rots, trans, self, groups)

@@ -322,12 +322,15 @@ def test_view_transform_fwd_bwd_vs_oracle(pkg, orc, cfg_name, B):
     gd, gf = orc.bev_pool_v2_backward(gout.permute(0, 2, 3, 4, 1).contiguous().numpy(), depth.numpy(), feat_cl,
                                       rd, rf, rb, exact=True)
     view = view.to(DEV)
-    for mode in ("api", "fused"):
+    for mode in ("api", "fused", "fused_groups"):
         d = depth.to(DEV).requires_grad_()
         f = feat.to(DEV).requires_grad_()
+        view.frame_groups = 1
         if mode == "api":
             bev = view.voxel_pooling_v2(view.get_geometry(rots.to(DEV), trans.to(DEV)), d, f)
         else:
+            if mode == "fused_groups":      # independent frame groups on concurrent streams
+                view.frame_groups = 2 if B % 2 == 0 else 1
             bev = view(d, f, rots.to(DEV), trans.to(DEV))
         assert bev.shape == (B, C, Z, Y, X)
         assert rel_to_max(bev.detach().permute(0, 2, 3, 4, 1).cpu().numpy(), ref) <= TOL, mode
