@@ -21,6 +21,8 @@
  *   bevpool_v2_forward_dense /    bev_pool.py:27 (zeros) + :29 (kernel) + :91 (permute) in one pass;
  *   bevpool_v2_backward_dense     bev_pool.py:47-57,67-70 (argsort, zeros, kernel) in one pass
  *
+ *   bevpool_v1_forward / _backward ops/bev_pool/src/bev_pool.cpp:27-94, src/bev_pool_cuda.cu:20-84 (v1 op)
+ *
  * Argument order note: like the reference's native entry points, interval_lengths
  * precedes interval_starts here (bev_pool.cpp:37-38), the opposite of the Python API.
  */
@@ -165,6 +167,19 @@ int bevpool_v2_backward_dense(const void* out_grad, void* depth_grad, void* feat
  * to_channels_last != 0: src is BCZYX, dst is BZYXC; else the reverse. */
 int bevpool_grid_transpose(const void* src, void* dst, int b, int c, int64_t zyx,
                            int to_channels_last, int dtype, void* stream);
+
+/* ------------------------------------------------------------------ v1 op (ops/bev_pool)
+ * Replaces bev_pool_forward / bev_pool_backward of ops/bev_pool/src/bev_pool.cpp:27-94 and the kernels of
+ * ops/bev_pool/src/bev_pool_cuda.cu:20-84. x is [n, c], already multiplied by depth and sorted by voxel rank;
+ * geom_feats is int32 [n, 4] = (h, w, d, b) indices as the reference kernel reads them (cur_geom_feats[0..3]);
+ * out / out_grad are [b, d, h, w, c]. `out` is PRE-ZEROED by the caller (the reference allocates torch::zeros);
+ * x_grad is fully written for every row that belongs to an interval. */
+int bevpool_v1_forward(const void* x, const int32_t* geom_feats, const int32_t* interval_lengths,
+                       const int32_t* interval_starts, void* out, int b, int d, int h, int w, int64_t n,
+                       int64_t n_intervals, int c, int dtype, void* stream);
+int bevpool_v1_backward(const void* out_grad, const int32_t* geom_feats, const int32_t* interval_lengths,
+                        const int32_t* interval_starts, void* x_grad, int b, int d, int h, int w, int64_t n,
+                        int64_t n_intervals, int c, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,8 @@ SIGNATURES = {
     "bevpool_v2_forward_dense": (c_int, [c_void_p] * 7 + [c_i64, c_void_p, c_int, c_i64, c_i64, c_int, c_int, c_int,
                                                           c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "bevpool_v2_backward_dense": (c_int, [c_void_p] * 6 + [c_int] * 8 + [c_void_p]),
+    "bevpool_v1_forward": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_i64, c_i64, c_int, c_int, c_void_p]),
+    "bevpool_v1_backward": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_i64, c_i64, c_int, c_int, c_void_p]),
     "bevpool_grid_transpose": (c_int, [c_void_p, c_void_p, c_int, c_int, c_i64, c_int, c_int, c_void_p]),
 }
 

@@ -267,6 +267,78 @@ transpose_to_channels_last_kernel(const T* __restrict__ src, T* __restrict__ dst
   }
 }
 
+// ------------------------------------------------------------------------------------------ v1 bev_pool
+// ops/bev_pool (MIT-BEVFusion style): features are already multiplied by depth and SORTED by voxel rank, so an
+// interval is a run of consecutive rows of x. out[b][d][h][w][:] = sum of the interval's rows, with
+// (h, w, d, b) = geom_feats[start] (note the index order of the reference kernel, bev_pool_cuda.cu:36-38).
+// One warp per interval, lanes span channels as 128-bit vectors, rows are streamed (each is read exactly once).
+template <typename T>
+__global__ void __launch_bounds__(kPoolThreads)
+pool_v1_fwd_kernel(const T* __restrict__ x, const int* __restrict__ geom, const int* __restrict__ starts,
+                   const int* __restrict__ lengths, int64_t n_intervals, int d, int h, int w, int c, T* __restrict__ out) {
+  const int lane = lane_id();
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool vec = (c & 3) == 0;
+  for (int64_t k = warp0; k < n_intervals; k += n_warps) {
+    const int s = __ldg(starts + k), len = __ldg(lengths + k);
+    const int4 g = *reinterpret_cast<const int4*>(geom + 4 * (int64_t)s);
+    const int64_t obase = ((((int64_t)g.w * d + g.z) * h + g.x) * w + g.y) * c;
+    if (vec) {
+      for (int ch = 4 * lane; ch < c; ch += 128) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int i = 0;
+        for (; i + 4 <= len; i += 4) {
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = Vec4<T>::load_stream(x, (int64_t)(s + i + u) * c + ch);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        }
+        for (; i < len; ++i) {
+          const float4 v = Vec4<T>::load_stream(x, (int64_t)(s + i) * c + ch);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        Vec4<T>::store(out, obase + ch, acc);
+      }
+    } else {
+      for (int ch = lane; ch < c; ch += 32) {
+        float acc = 0.f;
+        for (int i = 0; i < len; ++i) acc += Vec4<T>::load1(x, (int64_t)(s + i) * c + ch);
+        Vec4<T>::store1(out, obase + ch, acc);
+      }
+    }
+  }
+}
+
+// x_grad[row] = out_grad[voxel of the row's interval]: one row load, len row stores.
+template <typename T>
+__global__ void __launch_bounds__(kPoolThreads)
+pool_v1_bwd_kernel(const T* __restrict__ og, const int* __restrict__ geom, const int* __restrict__ starts,
+                   const int* __restrict__ lengths, int64_t n_intervals, int d, int h, int w, int c,
+                   T* __restrict__ x_grad) {
+  const int lane = lane_id();
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool vec = (c & 3) == 0;
+  for (int64_t k = warp0; k < n_intervals; k += n_warps) {
+    const int s = __ldg(starts + k), len = __ldg(lengths + k);
+    const int4 g = *reinterpret_cast<const int4*>(geom + 4 * (int64_t)s);
+    const int64_t obase = ((((int64_t)g.w * d + g.z) * h + g.x) * w + g.y) * c;
+    if (vec) {
+      for (int ch = 4 * lane; ch < c; ch += 128) {
+        const float4 v = Vec4<T>::load(og, obase + ch);
+        for (int i = 0; i < len; ++i) Vec4<T>::store(x_grad, (int64_t)(s + i) * c + ch, v);
+      }
+    } else {
+      for (int ch = lane; ch < c; ch += 32) {
+        const float v = Vec4<T>::load1(og, obase + ch);
+        for (int i = 0; i < len; ++i) Vec4<T>::store1(x_grad, (int64_t)(s + i) * c + ch, v);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static inline int grid_for_warps(int64_t n_items, int warps_per_block, int max_blocks) {
   int64_t b = (n_items + warps_per_block - 1) / warps_per_block;
@@ -402,4 +474,51 @@ extern "C" int bevpool_grid_transpose(const void* src, void* dst, int b, int c, 
     return transpose_t<__nv_bfloat16>(src, dst, b, (int)zyx, c, st);
   }
   return BEVPOOL_ERR_BAD_ARG;
+}
+
+extern "C" int bevpool_v1_forward(const void* x, const int32_t* geom_feats, const int32_t* interval_lengths,
+                                  const int32_t* interval_starts, void* out, int b, int d, int h, int w, int64_t n,
+                                  int64_t n_intervals, int c, int dtype, void* stream) {
+  if (b < 0 || d < 0 || h < 0 || w < 0 || n < 0 || n_intervals < 0) return BEVPOOL_ERR_BAD_ARG;
+  if (c <= 0) return BEVPOOL_ERR_BAD_CHANNELS;
+  if (n_intervals == 0) return BEVPOOL_OK;
+  if (!x || !geom_feats || !interval_lengths || !interval_starts || !out) return BEVPOOL_ERR_BAD_ARG;
+  if ((uintptr_t)geom_feats % 16 || (c % 4 == 0 && ((uintptr_t)x % 16 || (uintptr_t)out % 16))) return BEVPOOL_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for_warps(n_intervals, kPoolWarps, kNumSMs * 32);
+  if (dtype == BEVPOOL_F32)
+    pool_v1_fwd_kernel<float><<<grid, kPoolThreads, 0, st>>>((const float*)x, geom_feats, interval_starts, interval_lengths,
+                                                              n_intervals, d, h, w, c, (float*)out);
+  else if (dtype == BEVPOOL_BF16)
+    pool_v1_fwd_kernel<__nv_bfloat16><<<grid, kPoolThreads, 0, st>>>((const __nv_bfloat16*)x, geom_feats, interval_starts,
+                                                                      interval_lengths, n_intervals, d, h, w, c,
+                                                                      (__nv_bfloat16*)out);
+  else
+    return BEVPOOL_ERR_BAD_ARG;
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int bevpool_v1_backward(const void* out_grad, const int32_t* geom_feats, const int32_t* interval_lengths,
+                                   const int32_t* interval_starts, void* x_grad, int b, int d, int h, int w, int64_t n,
+                                   int64_t n_intervals, int c, int dtype, void* stream) {
+  if (b < 0 || d < 0 || h < 0 || w < 0 || n < 0 || n_intervals < 0) return BEVPOOL_ERR_BAD_ARG;
+  if (c <= 0) return BEVPOOL_ERR_BAD_CHANNELS;
+  if (n_intervals == 0) return BEVPOOL_OK;
+  if (!out_grad || !geom_feats || !interval_lengths || !interval_starts || !x_grad) return BEVPOOL_ERR_BAD_ARG;
+  if ((uintptr_t)geom_feats % 16 || (c % 4 == 0 && ((uintptr_t)x_grad % 16 || (uintptr_t)out_grad % 16)))
+    return BEVPOOL_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for_warps(n_intervals, kPoolWarps, kNumSMs * 32);
+  if (dtype == BEVPOOL_F32)
+    pool_v1_bwd_kernel<float><<<grid, kPoolThreads, 0, st>>>((const float*)out_grad, geom_feats, interval_starts,
+                                                              interval_lengths, n_intervals, d, h, w, c, (float*)x_grad);
+  else if (dtype == BEVPOOL_BF16)
+    pool_v1_bwd_kernel<__nv_bfloat16><<<grid, kPoolThreads, 0, st>>>((const __nv_bfloat16*)out_grad, geom_feats,
+                                                                      interval_starts, interval_lengths, n_intervals, d, h,
+                                                                      w, c, (__nv_bfloat16*)x_grad);
+  else
+    return BEVPOOL_ERR_BAD_ARG;
+  count_launch();
+  return launch_status();
 }

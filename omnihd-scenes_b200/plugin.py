@@ -18,6 +18,7 @@ from . import bev_pool as _bev_pool
 from . import view_transform as _vt
 
 REF_MODULE = "projects.mmdet3d_plugin.ops.bev_pool_v2.bev_pool"
+REF_MODULE_V1 = "projects.mmdet3d_plugin.ops.bev_pool.bev_pool"   # the plugin __init__ imports this one (:20)
 
 
 def install(force=False):
@@ -34,6 +35,12 @@ def install(force=False):
     parent = sys.modules.get("projects.mmdet3d_plugin.ops.bev_pool_v2")
     if parent is not None:
         parent.bev_pool = mod
+    # v1 op: `from .ops.bev_pool import *` in mmdet3d_plugin/__init__.py:20 needs bev_pool_ext built otherwise
+    from . import bev_pool_v1 as _v1
+    if REF_MODULE_V1 not in sys.modules or force:
+        m1 = types.ModuleType(REF_MODULE_V1)
+        m1.bev_pool, m1.QuickCumsumCuda, m1.__all__ = _v1.bev_pool, _v1.QuickCumsumCuda, ["bev_pool"]
+        sys.modules[REF_MODULE_V1] = m1
     return mod
 
 

@@ -115,3 +115,34 @@ void oracle_voxel_rank(const float *coor, int64_t n_points, int64_t points_per_f
         rank_out[i] = ok ? b * (nx[2] * nx[1] * nx[0]) + v[2] * (nx[1] * nx[0]) + v[1] * nx[0] + v[0] : -1;
     }
 }
+
+/*
+ * v1 op (ops/bev_pool): follows bev_pool_cuda.cu:20-42 (forward) and :61-84 (backward).
+ * x is [n, c] sorted by rank; geom is int[n, 4]; out / out_grad are [b, d, h, w, c].
+ */
+void oracle_bev_pool_v1_fwd(int d, int h, int w, int c, int n_intervals, const float *x, const int *geom,
+                            const int *starts, const int *lengths, float *out)
+{
+    for (int k = 0; k < n_intervals; ++k) {
+        const int s = starts[k], len = lengths[k];
+        const int *g = geom + 4 * (int64_t)s;
+        float *o = out + ((((int64_t)g[3] * d + g[2]) * h + g[0]) * w + g[1]) * c;
+        for (int ch = 0; ch < c; ++ch) {
+            float psum = 0.f;
+            for (int i = 0; i < len; ++i) psum += x[(int64_t)(s + i) * c + ch];
+            o[ch] = psum;
+        }
+    }
+}
+
+void oracle_bev_pool_v1_bwd(int d, int h, int w, int c, int n_intervals, const float *out_grad, const int *geom,
+                            const int *starts, const int *lengths, float *x_grad)
+{
+    for (int k = 0; k < n_intervals; ++k) {
+        const int s = starts[k], len = lengths[k];
+        const int *g = geom + 4 * (int64_t)s;
+        const float *o = out_grad + ((((int64_t)g[3] * d + g[2]) * h + g[0]) * w + g[1]) * c;
+        for (int i = 0; i < len; ++i)
+            for (int ch = 0; ch < c; ++ch) x_grad[(int64_t)(s + i) * c + ch] = o[ch];
+    }
+}

@@ -13,6 +13,7 @@ Each function cites the reference lines it follows (paths relative to
   prepare_v2           same :294-351
   bev_pool_v2_forward  ops/bev_pool_v2/src/bev_pool_cuda.cu:21-48  (+ zeros, ops/bev_pool_v2/bev_pool.py:27)
   bev_pool_v2_backward ops/bev_pool_v2/bev_pool.py:44-83 + src/bev_pool_cuda.cu:67-121
+  bev_pool_v1          ops/bev_pool/bev_pool.py:83-97 + ops/bev_pool/src/bev_pool_cuda.cu:20-84 (v1 op)
   cumsum_voxel_pooling cam_stream_lss_bevpoolv2.py:85-122 (QuickCumsum) inside upstream-LSS glue
                        — the CPU BASELINE, not a parity oracle (global cumsum loses precision)
 
@@ -187,6 +188,35 @@ def bev_pool_v2_backward(out_grad, depth, feat, ranks_depth, ranks_feat, ranks_b
                                   _p(rd, _i), _p(rf, _i), _p(rb, _i), _p(starts, _i), _p(lengths, _i),
                                   _p(dg, _f), _p(fg, _f), _i(1 if exact else 0))
     return dg, fg
+
+
+# --------------------------------------------------------------------------- v1 op
+def bev_pool_v1(feats, coords, B, D, H, W):
+    """ops/bev_pool/bev_pool.py:83-97 + src/bev_pool_cuda.cu:20-42: -> (out [B,C,D,H,W], order, starts, lengths)."""
+    feats = np.ascontiguousarray(feats, dtype=np.float32)
+    coords = np.asarray(coords).astype(np.int64)
+    ranks = coords[:, 0] * (W * D * B) + coords[:, 1] * (D * B) + coords[:, 2] * B + coords[:, 3]
+    order = np.argsort(ranks, kind="stable")
+    x = np.ascontiguousarray(feats[order])
+    geom = np.ascontiguousarray(coords[order].astype(np.int32))
+    starts, lengths = intervals_from_sorted(ranks[order])
+    c = x.shape[1]
+    out = np.zeros((B, D, H, W, c), dtype=np.float32)
+    _lib().oracle_bev_pool_v1_fwd(_i(D), _i(H), _i(W), _i(c), _i(starts.size), _p(x, _f), _p(geom, _i), _p(starts, _i),
+                                  _p(lengths, _i), _p(out, _f))
+    return out.transpose(0, 4, 1, 2, 3).copy(), order, geom, starts, lengths
+
+
+def bev_pool_v1_backward(out_grad_bcdhw, order, geom, starts, lengths, D, H, W):
+    """Gradient w.r.t. the ORIGINAL (unsorted) feats rows."""
+    og = np.ascontiguousarray(out_grad_bcdhw.transpose(0, 2, 3, 4, 1), dtype=np.float32)
+    c = og.shape[-1]
+    xg = np.zeros((order.size, c), dtype=np.float32)
+    _lib().oracle_bev_pool_v1_bwd(_i(D), _i(H), _i(W), _i(c), _i(starts.size), _p(og, _f), _p(geom, _i), _p(starts, _i),
+                                  _p(lengths, _i), _p(xg, _f))
+    out = np.zeros_like(xg)
+    out[order] = xg
+    return out
 
 
 # --------------------------------------------------------------------------- CPU baseline (torch)

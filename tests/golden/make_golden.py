@@ -178,6 +178,27 @@ def main():
     assert all(o is None for o in out)
     print("empty case -> 5 x None (reference behaviour confirmed)")
 
+    # v1 op (ops/bev_pool/bev_pool.py): the reference's own CPU QuickCumsum on seeded random points
+    v1_mod = types.ModuleType("projects.mmdet3d_plugin.ops.bev_pool")
+    v1_mod.__path__ = [os.path.join(REF, "projects/mmdet3d_plugin/ops/bev_pool")]
+    sys.modules["projects.mmdet3d_plugin.ops.bev_pool"] = v1_mod
+    sys.modules["projects.mmdet3d_plugin.ops.bev_pool.bev_pool_ext"] = _Permissive("bev_pool_ext")
+    v1_mod.bev_pool_ext = sys.modules["projects.mmdet3d_plugin.ops.bev_pool.bev_pool_ext"]
+    v1 = importlib.import_module("projects.mmdet3d_plugin.ops.bev_pool.bev_pool")
+    g = torch.Generator().manual_seed(5)
+    Bv, Dv, Hv, Wv, Cv, Nv = 2, 3, 12, 10, 8, 6000
+    feats = torch.randn(Nv, Cv, generator=g)
+    coords = torch.stack([torch.randint(0, Hv, (Nv,), generator=g), torch.randint(0, Wv, (Nv,), generator=g),
+                          torch.randint(0, Dv, (Nv,), generator=g), torch.randint(0, Bv, (Nv,), generator=g)], 1)
+    ranks = coords[:, 0] * (Wv * Dv * Bv) + coords[:, 1] * (Dv * Bv) + coords[:, 2] * Bv + coords[:, 3]
+    idx = ranks.argsort(stable=True)
+    xo, go = v1.QuickCumsum.apply(feats[idx], coords[idx], ranks[idx])
+    dense = torch.zeros(Bv, Dv, Hv, Wv, Cv)
+    dense[go[:, 3], go[:, 2], go[:, 0], go[:, 1]] = xo       # index order of bev_pool_cuda.cu:36-38
+    np.savez_compressed(os.path.join(HERE, "v1_bev_pool.npz"), feats=feats.numpy(), coords=coords.numpy(),
+                        dims=np.array([Bv, Dv, Hv, Wv]), pooled=dense.permute(0, 4, 1, 2, 3).contiguous().numpy())
+    print("v1 golden: intervals", xo.shape[0])
+
     # the reference's own KAT, transcribed (ops/bev_pool_v2/bev_pool.py:145-176)
     np.savez(os.path.join(HERE, "kat_bev_pool_v2.npz"),
              depth=np.array([0.3, 0.4, 0.2, 0.1, 0.7, 0.6, 0.8, 0.9], dtype=np.float32).reshape(1, 1, 2, 2, 2),

@@ -410,3 +410,31 @@ def test_errors_are_loud(pkg):
     assert lib.bevpool_v2_forward(0, 0, 0, 0, 0, 0, 0, 0, 5, 5, 0, 0, 0) == -2
     assert lib.bevpool_v2_forward_dense(16, 16, 16, 16, 0, 16, 16, 5, 0, 6, 1, 8, 8, 0, 0, 1, 0, 0, 0, 0) == -2     # C % 4
     assert lib.bevpool_v2_forward_dense(16, 16, 16, 16, 0, 16, 16, 5, 0, 8, 1, 8, 8, 0, 0, 1, 0, 0, 0, 0) == -1     # no ranks_feat, no dims
+
+
+# --------------------------------------------------------------------------------------- v1 op
+@pytest.mark.parametrize("C,N", [(8, 6000), (80, 50000), (6, 3000)])
+def test_v1_bev_pool_vs_oracle_and_reference_kernel(pkg, orc, C, N):
+    rng = np.random.default_rng(C)
+    B, D, H, W = 2, 3, 40, 36
+    feats = rng.standard_normal((N, C)).astype(np.float32)
+    coords = np.stack([rng.integers(0, H, N), rng.integers(0, W, N), rng.integers(0, D, N), rng.integers(0, B, N)], 1)
+    ref, order, geom, starts, lengths = orc.bev_pool_v1(feats, coords, B, D, H, W)
+    x = cu(feats).requires_grad_()
+    out = pkg.bev_pool_v1.bev_pool(x, cu(coords), B, D, H, W)
+    assert out.shape == (B, C, D, H, W) and out.is_contiguous()
+    assert np.array_equal(out.detach().cpu().numpy(), ref)        # same sequential summation order: bit-identical
+    og = rng.standard_normal(ref.shape).astype(np.float32)
+    out.backward(cu(og))
+    assert np.array_equal(x.grad.cpu().numpy(), orc.bev_pool_v1_backward(og, order, geom, starts, lengths, D, H, W))
+    # the reference's unmodified v1 kernels (oracle/_ref), same sorted inputs
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_bevpool_v1.so")
+    if os.path.exists(path):
+        lib = ctypes.CDLL(path)
+        xs, gs, st, ln = cu(feats[order]), cu(geom), cu(starts), cu(lengths)
+        o_ref = torch.zeros((B, D, H, W, C), device=DEV)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        torch.cuda.synchronize()
+        assert lib.ref_bev_pool_v1_fwd(B, D, H, W, N, C, starts.size, p(xs), p(gs), p(st), p(ln), p(o_ref)) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(o_ref.permute(0, 4, 1, 2, 3), out.detach())

@@ -140,3 +140,17 @@ def test_backward_is_gradient_of_forward(orc, golden):
         f = feat_cl.copy().reshape(-1)
         f[idx] += 0.5
         assert abs((loss(g["depth"], f.reshape(feat_cl.shape)) - base) / 0.5 - gf.reshape(-1)[idx]) < 2e-3 * max(1, abs(gf.reshape(-1)[idx]))
+
+
+def test_v1_bev_pool_matches_reference_cpu_quickcumsum(orc):
+    """ops/bev_pool (v1): the reference's own CPU QuickCumsum on seeded random points (global cumsum: 1e-5 of max)."""
+    g = np.load(os.path.join(GOLDEN, "v1_bev_pool.npz"))
+    B, D, H, W = (int(v) for v in g["dims"])
+    out, order, geom, starts, lengths = orc.bev_pool_v1(g["feats"], g["coords"], B, D, H, W)
+    assert out.shape == g["pooled"].shape
+    assert rel_to_max(out, g["pooled"]) <= 1e-5
+    # backward of a plain sum: every row receives the gradient of its voxel
+    og = np.random.default_rng(0).standard_normal(out.shape).astype(np.float32)
+    xg = orc.bev_pool_v1_backward(og, order, geom, starts, lengths, D, H, W)
+    c = g["coords"]
+    assert np.array_equal(xg, og[c[:, 3], :, c[:, 2], c[:, 0], c[:, 1]])
