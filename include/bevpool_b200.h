@@ -21,6 +21,7 @@
  *   bevpool_v2_forward_dense /    bev_pool.py:27 (zeros) + :29 (kernel) + :91 (permute) in one pass;
  *   bevpool_v2_backward_dense     bev_pool.py:47-57,67-70 (argsort, zeros, kernel) in one pass
  *
+ *   bevpool_lift_forward / _backward  bevfusion/detectors/cam_stream_lss_bevpoolv2.py:134-141 (+ :282)
  *   bevpool_v1_forward / _backward ops/bev_pool/src/bev_pool.cpp:27-94, src/bev_pool_cuda.cu:20-84 (v1 op)
  *
  * Argument order note: like the reference's native entry points, interval_lengths
@@ -180,6 +181,16 @@ int bevpool_v1_forward(const void* x, const int32_t* geom_feats, const int32_t* 
 int bevpool_v1_backward(const void* out_grad, const int32_t* geom_feats, const int32_t* interval_lengths,
                         const int32_t* interval_starts, void* x_grad, int b, int d, int h, int w, int64_t n,
                         int64_t n_intervals, int c, int dtype, void* stream);
+
+/* ------------------------------------------------------------------ lift head
+ * CamEncode.get_depth_feat (cam_stream_lss_bevpoolv2.py:134-141) fused with the NCHW->NHWC transpose of the
+ * context features (:282): x [BN, D+C, H, W] -> depth [BN, D, H, W] = softmax over the first D channels and
+ * feat = channels D..D+C-1 as [BN, H, W, C] (feat_channels_last != 0) or [BN, C, H, W]. One streaming pass each
+ * way; the backward applies the softmax Jacobian (dx = y * (g - sum_d g*y)) and the inverse transpose. D <= 256. */
+int bevpool_lift_forward(const void* x, void* depth, void* feat, int bn, int d, int c, int hw,
+                         int feat_channels_last, int dtype, void* stream);
+int bevpool_lift_backward(const void* depth, const void* depth_grad, const void* feat_grad, void* x_grad,
+                          int bn, int d, int c, int hw, int feat_channels_last, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,8 @@ SIGNATURES = {
     "bevpool_v2_backward_dense": (c_int, [c_void_p] * 6 + [c_int] * 8 + [c_void_p]),
     "bevpool_v1_forward": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_i64, c_i64, c_int, c_int, c_void_p]),
     "bevpool_v1_backward": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_i64, c_i64, c_int, c_int, c_void_p]),
+    "bevpool_lift_forward": (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
+    "bevpool_lift_backward": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     "bevpool_grid_transpose": (c_int, [c_void_p, c_void_p, c_int, c_int, c_i64, c_int, c_int, c_void_p]),
 }
 

@@ -192,10 +192,10 @@ class _FusedViewPool(torch.autograd.Function):
     The frame batch is cut into `groups` independent groups that run on concurrent streams."""
 
     @staticmethod
-    def forward(ctx, depth, feat, rots, trans, view, groups):
+    def forward(ctx, depth, feat, rots, trans, view, groups, feat_channels_last=False):
         B, N = trans.shape[:2]
         D, H, W = view.D, view.fH, view.fW
-        C = feat.shape[2]
+        C = feat.shape[4] if feat_channels_last else feat.shape[2]
         X, Y, Z = (int(v) for v in view.nx)
         depth = depth.contiguous()
         feat = feat.contiguous()
@@ -211,14 +211,17 @@ class _FusedViewPool(torch.autograd.Function):
             with torch.cuda.stream(st):
                 pr = _prepare_device(None, view.frustum, rots[sl], trans[sl], n, N, D, H, W, view.dx, view.bx, view.nx,
                                      feat.device, want_intervals=False)
-                feat_cl = feat.new_empty((pr.bn, H, W, C))
-                _launch_transpose(feat[sl], feat_cl, pr.bn, C, pr.hw, True)           # [BN,C,HW] -> [BN,HW,C]
+                if feat_channels_last:                                                # lift head already wrote NHWC
+                    feat_cl = feat[sl]
+                else:
+                    feat_cl = feat.new_empty((pr.bn, H, W, C))
+                    _launch_transpose(feat[sl], feat_cl, pr.bn, C, pr.hw, True)       # [BN,C,HW] -> [BN,HW,C]
                 vox_pt = _launch_voxel_table(pr.rb, pr.p0, pr.counts, n * Z * Y * X)
                 _launch_forward_dense(depth[sl], feat_cl, out[sl], pr.rd, None, pr.rb, vox_pt, n, Z * Y, X,
                                       _lib.LAYOUT_BCZYX, dhw=D * pr.hw, hw=pr.hw, n_points=pr.p0, counts_dev=pr.counts)
             saved.append((pr, feat_cl))
         fork.join()
-        ctx.saved, ctx.dims, ctx.groups = saved, (B, N, C, D, H, W, X, Y, Z), groups
+        ctx.saved, ctx.dims, ctx.groups, ctx.feat_cl = saved, (B, N, C, D, H, W, X, Y, Z), groups, feat_channels_last
         ctx.save_for_backward(depth)
         return out
 
@@ -231,7 +234,7 @@ class _FusedViewPool(torch.autograd.Function):
         dt = ctx.saved[0][1].dtype
         out_grad = out_grad.contiguous().to(dt)
         depth_grad = torch.empty_like(depth)
-        feat_grad = depth.new_empty((B, N, C, H, W))
+        feat_grad = depth.new_empty((B, N, H, W, C) if ctx.feat_cl else (B, N, C, H, W))
         lib = _lib.load()
         fork = _Fork(depth.device, groups)
         for g, st in enumerate(fork.streams):
@@ -242,10 +245,11 @@ class _FusedViewPool(torch.autograd.Function):
                 _launch_transpose(out_grad[sl], og_cl, n, C, Z * Y * X, True)
                 _lib.check(lib.bevpool_v2_backward_dense(_ptr(og_cl), _ptr(depth_grad[sl]), _ptr(feat_grad[sl]),
                                                          _ptr(depth[sl]), _ptr(feat_cl), _ptr(pr.point_rank), pr.bn, D, H,
-                                                         W, C, 1, 1 if Z == 1 else 0, _dtype_code(feat_cl), _stream()),
+                                                         W, C, 0 if ctx.feat_cl else 1, 1 if Z == 1 else 0,
+                                                         _dtype_code(feat_cl), _stream()),
                            "bevpool_v2_backward_dense")
         fork.join()
-        return depth_grad, feat_grad, None, None, None, None
+        return depth_grad, feat_grad, None, None, None, None, None
 
 
 class LSSViewTransform(nn.Module):
@@ -306,17 +310,31 @@ class LSSViewTransform(nn.Module):
         return self.voxel_pooling_v2(self.get_geometry(rots, trans), depth, feat)
 
     # -- fused path ---------------------------------------------------------------------------
-    def forward(self, depth, feat, rots, trans):
+    def forward(self, depth, feat, rots, trans, feat_channels_last=False):
         """Fused view transform: geometry is never materialised, nothing synchronises with the host.
-        depth [B,N,D,fH,fW], feat [B,N,C,fH,fW] -> [B,C,Z,Y,X] (all zeros if no point is in range)."""
+        depth [B,N,D,fH,fW], feat [B,N,C,fH,fW] ([B,N,fH,fW,C] with feat_channels_last, as `lift` returns it)
+        -> [B,C,Z,Y,X] (all zeros if no point is in range)."""
         _check_f32_cuda("rots", rots, (3, 3))
         _check_f32_cuda("trans", trans, (3,))
         B, N = trans.shape[:2]
         D, H, W = self.D, self.fH, self.fW
         if tuple(depth.shape) != (B, N, D, H, W):
             raise ValueError(f"depth must be {(B, N, D, H, W)}, got {tuple(depth.shape)}")
-        C = feat.shape[2]
+        C = feat.shape[4] if feat_channels_last else feat.shape[2]
+        want = (B, N, H, W, C) if feat_channels_last else (B, N, C, H, W)
+        if tuple(feat.shape) != want:
+            raise ValueError(f"feat must be {want}, got {tuple(feat.shape)}")
         if C % 4:
             raise ValueError("the fused path needs C % 4 == 0; use voxel_pooling_v2 for other channel counts")
         groups = self.frame_groups if (self.frame_groups > 1 and B % self.frame_groups == 0) else 1
-        return _FusedViewPool.apply(depth, feat, rots, trans, self, groups)
+        return _FusedViewPool.apply(depth, feat, rots, trans, self, groups, feat_channels_last)
+
+    def lift_splat(self, x, rots, trans, C):
+        """Depthnet output x [B*N, D+C, fH, fW] -> BEV grid [B,C,Z,Y,X]: fused softmax/split/transpose head
+        (`lift.get_depth_feat`) feeding the fused view transform. Returns (bev, depth [B*N, D, fH, fW])."""
+        from .lift import get_depth_feat
+        B, N = trans.shape[:2]
+        depth, feat_cl = get_depth_feat(x, self.D, C, channels_last=True)
+        bev = self.forward(depth.view(B, N, self.D, self.fH, self.fW), feat_cl.view(B, N, self.fH, self.fW, C), rots, trans,
+                           feat_channels_last=True)
+        return bev, depth

@@ -190,6 +190,23 @@ def bev_pool_v2_backward(out_grad, depth, feat, ranks_depth, ranks_feat, ranks_b
     return dg, fg
 
 
+# --------------------------------------------------------------------------- lift head
+def lift_head(x, D, C):
+    """CamEncode.get_depth_feat (cam_stream_lss_bevpoolv2.py:134-141) after the depthnet: softmax over the first D
+    channels (float64 inside, rounded once) and the C context channels as a slice. -> (depth, feat) NCHW."""
+    x = np.asarray(x, dtype=np.float32)
+    z = x[:, :D].astype(np.float64)
+    e = np.exp(z - z.max(axis=1, keepdims=True))
+    return (e / e.sum(axis=1, keepdims=True)).astype(np.float32), x[:, D:D + C].copy()
+
+
+def lift_head_backward(depth, depth_grad, feat_grad):
+    """Softmax Jacobian (dx = y * (g - sum_d g*y)) and the pass-through of the context gradient. -> x_grad NCHW."""
+    y, g = depth.astype(np.float64), depth_grad.astype(np.float64)
+    dx = y * (g - (g * y).sum(axis=1, keepdims=True))
+    return np.concatenate([dx.astype(np.float32), np.asarray(feat_grad, dtype=np.float32)], axis=1)
+
+
 # --------------------------------------------------------------------------- v1 op
 def bev_pool_v1(feats, coords, B, D, H, W):
     """ops/bev_pool/bev_pool.py:83-97 + src/bev_pool_cuda.cu:20-42: -> (out [B,C,D,H,W], order, starts, lengths)."""

@@ -199,6 +199,24 @@ def main():
                         dims=np.array([Bv, Dv, Hv, Wv]), pooled=dense.permute(0, 4, 1, 2, 3).contiguous().numpy())
     print("v1 golden: intervals", xo.shape[0])
 
+    # lift head: the reference's CamEncode.get_depth_feat (:134-141) with the 1x1 depthnet replaced by identity,
+    # plus its autograd gradients for seeded upstream gradients
+    torch.manual_seed(11)
+    Dl, Cl, BNl, Hl, Wl = 13, 8, 3, 5, 7
+    enc = ref.CamEncode(Dl, Cl, 4)
+    enc.depthnet = torch.nn.Identity()
+    xl = (torch.randn(BNl, Dl + Cl, Hl, Wl) * 3).requires_grad_()
+    dl, fl = enc.get_depth_feat(xl)
+    gd, gf = torch.randn_like(dl), torch.randn_like(fl)
+    (dl * gd).sum().backward(retain_graph=True)
+    gx_d = xl.grad.clone()
+    xl.grad = None
+    (fl * gf).sum().backward()
+    np.savez_compressed(os.path.join(HERE, "lift_head.npz"), x=xl.detach().numpy(), depth=dl.detach().numpy(),
+                        feat=fl.detach().numpy(), depth_grad=gd.numpy(), feat_grad=gf.numpy(),
+                        x_grad=(gx_d + xl.grad).numpy(), dims=np.array([Dl, Cl]))
+    print("lift golden", tuple(dl.shape), tuple(fl.shape))
+
     # the reference's own KAT, transcribed (ops/bev_pool_v2/bev_pool.py:145-176)
     np.savez(os.path.join(HERE, "kat_bev_pool_v2.npz"),
              depth=np.array([0.3, 0.4, 0.2, 0.1, 0.7, 0.6, 0.8, 0.9], dtype=np.float32).reshape(1, 1, 2, 2, 2),

@@ -438,3 +438,72 @@ def test_v1_bev_pool_vs_oracle_and_reference_kernel(pkg, orc, C, N):
         assert lib.ref_bev_pool_v1_fwd(B, D, H, W, N, C, starts.size, p(xs), p(gs), p(st), p(ln), p(o_ref)) == 0
         torch.cuda.synchronize()
         assert torch.equal(o_ref.permute(0, 4, 1, 2, 3), out.detach())
+
+
+# ------------------------------------------------------------------------------------------ lift head (§8(f) rank 2)
+def test_lift_head_vs_reference_golden(pkg, orc):
+    """get_depth_feat against the reference's CamEncode output and gradients, both feature layouts."""
+    g = load("lift_head")
+    D, C = (int(v) for v in g["dims"])
+    for cl in (False, True):
+        x = cu(g["x"]).requires_grad_()
+        depth, feat = pkg.get_depth_feat(x, D, C, channels_last=cl)
+        f_nchw = feat.permute(0, 3, 1, 2) if cl else feat
+        assert rel_to_max(depth.detach().cpu().numpy(), g["depth"]) <= TOL
+        assert np.array_equal(f_nchw.detach().cpu().numpy(), g["feat"])
+        gf = cu(g["feat_grad"])
+        torch.autograd.backward([depth, feat], [cu(g["depth_grad"]), gf.permute(0, 2, 3, 1).contiguous() if cl else gf])
+        assert rel_to_max(x.grad.cpu().numpy(), g["x_grad"]) <= TOL
+    assert rel_to_max(pkg.get_depth_dist(cu(g["x"])).cpu().numpy(), orc.lift_head(g["x"], g["x"].shape[1], 0)[0]) <= TOL
+
+
+@pytest.mark.parametrize("D,C,H,W,dt", [(59, 80, 16, 44, torch.float32), (118, 80, 32, 88, torch.bfloat16),
+                                         (88, 32, 9, 13, torch.float32), (256, 4, 3, 5, torch.float32),
+                                         (1, 132, 2, 33, torch.float32)])
+def test_lift_head_shapes_vs_oracle(pkg, orc, D, C, H, W, dt):
+    """BASELINE lift shapes, ragged pixel tails (H*W % 32 != 0), the D limit, extra trailing channels, bf16 io."""
+    rng = np.random.default_rng(D * 1000 + C)
+    BN = 5
+    x = (rng.standard_normal((BN, D + C + 3, H, W)) * 4).astype(np.float32)
+    xt = cu(x).to(dt)
+    xin = xt.float().cpu().numpy()                                     # what the kernel actually reads
+    depth_ref, feat_ref = orc.lift_head(xin, D, C)
+    tol = TOL if dt == torch.float32 else 2 ** -8                      # bf16: one rounding of outputs in [0, 1]
+    xr = xt.clone().requires_grad_()
+    depth, feat = pkg.get_depth_feat(xr, D, C, channels_last=True)
+    assert depth.dtype == dt and feat.shape == (BN, H, W, C)
+    assert rel_to_max(depth.detach().float().cpu().numpy(), depth_ref) <= tol
+    assert np.array_equal(feat.detach().float().permute(0, 3, 1, 2).cpu().numpy(), feat_ref)
+    gd = rng.standard_normal(depth_ref.shape).astype(np.float32)
+    gf = rng.standard_normal(feat_ref.shape).astype(np.float32)
+    gdt, gft = cu(gd).to(dt), cu(gf).to(dt)
+    torch.autograd.backward([depth, feat], [gdt, gft.permute(0, 2, 3, 1).contiguous()])
+    want = orc.lift_head_backward(depth.detach().float().cpu().numpy(), gdt.float().cpu().numpy(), gft.float().cpu().numpy())
+    got = xr.grad.float().cpu().numpy()
+    assert got.shape == x.shape and np.all(got[:, D + C:] == 0)        # unused trailing channels get zero gradient
+    assert rel_to_max(got[:, :D + C], want) <= tol
+    with pytest.raises(RuntimeError, match="bad argument"):
+        pkg.get_depth_feat(cu(np.zeros((1, 300, 2, 2), np.float32)), 257, 4)
+
+
+def test_lift_splat_equals_separate_stages(pkg):
+    """lift_splat (fused head -> channels-last features -> fused pool, no transposes) gives bit-identical BEV grids
+    and input gradients within fp32 summation noise of torch.softmax + slice + LSSViewTransform.forward."""
+    cfg = pkg.synthetic.CONFIGS["bevdet_r50_b8"]
+    B, N, C = 2, cfg.n_cams, cfg.channels
+    view = pkg.LSSViewTransform.from_config(cfg).to(DEV)
+    rots, trans = pkg.synthetic.camera_ring(B, N, cfg.final_dim, seed=3)
+    rots, trans = rots.to(DEV), trans.to(DEV)
+    torch.manual_seed(5)
+    x = torch.randn(B * N, view.D + C, view.fH, view.fW, device=DEV)
+    gout = torch.randn(B, C, *[int(v) for v in view.nx.flip(0)], device=DEV)
+    xa = x.clone().requires_grad_()
+    bev_a, depth_a = view.lift_splat(xa, rots, trans, C)
+    bev_a.backward(gout)
+    xb = x.clone().requires_grad_()
+    depth_b = xb[:, :view.D].softmax(dim=1)
+    bev_b = view(depth_b.view(B, N, view.D, view.fH, view.fW), xb[:, view.D:].reshape(B, N, C, view.fH, view.fW), rots, trans)
+    bev_b.backward(gout)
+    assert rel_to_max(depth_a.detach().cpu().numpy(), depth_b.detach().cpu().numpy()) <= TOL
+    assert rel_to_max(bev_a.detach().cpu().numpy(), bev_b.detach().cpu().numpy()) <= TOL
+    assert rel_to_max(xa.grad.cpu().numpy(), xb.grad.cpu().numpy()) <= TOL

@@ -154,3 +154,15 @@ def test_v1_bev_pool_matches_reference_cpu_quickcumsum(orc):
     xg = orc.bev_pool_v1_backward(og, order, geom, starts, lengths, D, H, W)
     c = g["coords"]
     assert np.array_equal(xg, og[c[:, 3], :, c[:, 2], c[:, 0], c[:, 1]])
+
+
+def test_lift_head_matches_reference_camencode(orc):
+    """§8(f) rank 2: CamEncode.get_depth_feat run from the reference itself (identity depthnet) and its autograd
+    gradients; the oracle computes the softmax in float64, so 1e-6 of max is fp32 rounding on the reference side."""
+    g = np.load(os.path.join(GOLDEN, "lift_head.npz"))
+    D, C = (int(v) for v in g["dims"])
+    depth, feat = orc.lift_head(g["x"], D, C)
+    assert rel_to_max(depth, g["depth"]) <= 1e-6 and np.array_equal(feat, g["feat"])
+    assert np.allclose(depth.sum(axis=1), 1.0, atol=1e-6)
+    xg = orc.lift_head_backward(depth, g["depth_grad"], g["feat_grad"])
+    assert rel_to_max(xg, g["x_grad"]) <= 1e-6
