@@ -249,6 +249,26 @@ def run_native_arm(args):
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
 
+    # ---- (1b) variant, reported beside the headline (never instead of it): the same step with the BEV grid and
+    # its gradient in torch.channels_last_3d (what a channels-last conv stack produces/consumes) — same values,
+    # both layout passes gone. The headline `value` stays on the reference's contiguous [B,C,Z,Y,X] contract.
+    variants = {}
+    if not args.no_variants:
+        vg = []
+        for s in sets:
+            s["gout_cl"] = s["gout"].contiguous(memory_format=torch.channels_last_3d)
+            s["depth"].grad = None
+            s["feat"].grad = None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                s["bev_cl"] = view(s["depth"], s["feat"], s["rots"], s["trans"], memory_format=torch.channels_last_3d)
+                s["bev_cl"].backward(s["gout_cl"])
+            vg.append(g)
+        torch.cuda.synchronize()
+        ms_v = timed(lambda i: vg[i % N_BUFFER_SETS].replay(), args.steps, max(args.warmup, 3))
+        variants["channels_last_3d_grid"] = {"value": world * B * args.steps / (ms_v * 1e-3), "unit": UNIT,
+                                             "ms_per_step": ms_v / args.steps}
+
     # ---- (2) e2e: pinned host buffers -> H2D -> graph -> D2H, every step, same public API
     out_host = [dict(bev=torch.empty((B, C, Z, Y, X), dtype=dt_t).pin_memory(),
                      dg=torch.empty((B, N, D, H, W), dtype=dt_t).pin_memory(),
@@ -436,7 +456,7 @@ def run_native_arm(args):
                 "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "variants": variants,
     }))
     if world > 1:
         dist.destroy_process_group()
@@ -464,6 +484,7 @@ def main():
     ap.add_argument("--config", default=WORKLOAD)
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU (default: the config's batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the channels_last_3d variant measurement")
     ap.add_argument("--frame-groups", type=int, default=4,
                     help="independent frame groups run on concurrent streams inside one step (1 = single stream)")
     args = ap.parse_args()

@@ -14,6 +14,8 @@ voxel_pooling_v2 and s2c — without the conv nets around them (out of scope).
 
 Device work is done by csrc/prepare.cu and csrc/pool.cu through the C ABI.
 """
+import os
+
 import torch
 from torch import nn
 
@@ -184,6 +186,15 @@ class _Fork:
                 self.cur.wait_stream(st)
 
 
+def _column_hint(Z):
+    """Which sort-free backward kernel to prefer: the joint-column walk pays when vertically adjacent pixels
+    share voxels (always for Z == 1). BEVPOOL_BWD_KERNEL=joint|block overrides (measurement only)."""
+    env = os.environ.get("BEVPOOL_BWD_KERNEL")
+    if env in ("joint", "block"):
+        return 1 if env == "joint" else 0
+    return 1 if Z == 1 else 0
+
+
 class _FusedViewPool(torch.autograd.Function):
     """geometry -> rank -> sort -> pool with no host synchronisation: point counts stay on the device
     (counts_dev), buffers are worst-case sized. Takes feat as the neck produces it ([B,N,C,H,W]); the
@@ -192,7 +203,7 @@ class _FusedViewPool(torch.autograd.Function):
     The frame batch is cut into `groups` independent groups that run on concurrent streams."""
 
     @staticmethod
-    def forward(ctx, depth, feat, rots, trans, view, groups, feat_channels_last=False):
+    def forward(ctx, depth, feat, rots, trans, view, groups, feat_channels_last=False, s2c=False):
         B, N = trans.shape[:2]
         D, H, W = view.D, view.fH, view.fW
         C = feat.shape[4] if feat_channels_last else feat.shape[2]
@@ -202,7 +213,14 @@ class _FusedViewPool(torch.autograd.Function):
         if depth.dtype != feat.dtype or depth.dtype not in (torch.float32, torch.bfloat16):
             depth, feat = depth.float(), feat.float()
         rots, trans = rots.contiguous(), trans.contiguous()
-        out = feat.new_empty((B, C, Z, Y, X))
+        # s2c (reference :363-365) folds Z into the channel axis: [B, Z*C, Y, X]. Same kernels, the layout pass
+        # just treats every (frame, z) plane as a frame of Y rows.
+        # s2c == "channels_last": the grid stays in the kernels' own [B,Z,Y,X,C] order and is returned as a
+        # [B,C,Z,Y,X] VIEW of it (torch.channels_last_3d strides): no layout pass at all.
+        cl_out = s2c == "channels_last"
+        s2c = bool(s2c) and not cl_out
+        out = feat.new_empty((B, Z, Y, X, C) if cl_out else (B, Z * C, Y, X) if s2c else (B, C, Z, Y, X))
+        planes, rows = (Z, Y) if s2c else (1, Z * Y)
         n = B // groups
         saved = []
         fork = _Fork(feat.device, groups)
@@ -217,13 +235,14 @@ class _FusedViewPool(torch.autograd.Function):
                     feat_cl = feat.new_empty((pr.bn, H, W, C))
                     _launch_transpose(feat[sl], feat_cl, pr.bn, C, pr.hw, True)       # [BN,C,HW] -> [BN,HW,C]
                 vox_pt = _launch_voxel_table(pr.rb, pr.p0, pr.counts, n * Z * Y * X)
-                _launch_forward_dense(depth[sl], feat_cl, out[sl], pr.rd, None, pr.rb, vox_pt, n, Z * Y, X,
-                                      _lib.LAYOUT_BCZYX, dhw=D * pr.hw, hw=pr.hw, n_points=pr.p0, counts_dev=pr.counts)
+                _launch_forward_dense(depth[sl], feat_cl, out[sl], pr.rd, None, pr.rb, vox_pt, n * planes, rows, X,
+                                      _lib.LAYOUT_BZYXC if cl_out else _lib.LAYOUT_BCZYX, dhw=D * pr.hw, hw=pr.hw,
+                                      n_points=pr.p0, counts_dev=pr.counts)
             saved.append((pr, feat_cl))
         fork.join()
-        ctx.saved, ctx.dims, ctx.groups, ctx.feat_cl = saved, (B, N, C, D, H, W, X, Y, Z), groups, feat_channels_last
+        ctx.saved, ctx.dims, ctx.groups, ctx.feat_cl, ctx.s2c = saved, (B, N, C, D, H, W, X, Y, Z), groups, feat_channels_last, s2c
         ctx.save_for_backward(depth)
-        return out
+        return out.permute(0, 4, 1, 2, 3) if cl_out else out
 
     @staticmethod
     def backward(ctx, out_grad):
@@ -232,7 +251,9 @@ class _FusedViewPool(torch.autograd.Function):
         groups = ctx.groups
         n = B // groups
         dt = ctx.saved[0][1].dtype
-        out_grad = out_grad.contiguous().to(dt)
+        # a channels_last_3d gradient ([B,Z,Y,X,C] in memory) is consumed as it is; anything else is transposed
+        og_is_cl = (not ctx.s2c) and out_grad.dim() == 5 and out_grad.permute(0, 2, 3, 4, 1).is_contiguous()
+        out_grad = (out_grad.permute(0, 2, 3, 4, 1) if og_is_cl else out_grad.contiguous()).to(dt)
         depth_grad = torch.empty_like(depth)
         feat_grad = depth.new_empty((B, N, H, W, C) if ctx.feat_cl else (B, N, C, H, W))
         lib = _lib.load()
@@ -241,15 +262,20 @@ class _FusedViewPool(torch.autograd.Function):
             sl = slice(g * n, (g + 1) * n)
             pr, feat_cl = ctx.saved[g]
             with torch.cuda.stream(st):
-                og_cl = out_grad.new_empty((n, Z, Y, X, C))
-                _launch_transpose(out_grad[sl], og_cl, n, C, Z * Y * X, True)
+                og_cl = out_grad[sl] if og_is_cl else out_grad.new_empty((n, Z, Y, X, C))
+                if og_is_cl:
+                    pass
+                elif ctx.s2c:
+                    _launch_transpose(out_grad[sl], og_cl, n * Z, C, Y * X, True)
+                else:
+                    _launch_transpose(out_grad[sl], og_cl, n, C, Z * Y * X, True)
                 _lib.check(lib.bevpool_v2_backward_dense(_ptr(og_cl), _ptr(depth_grad[sl]), _ptr(feat_grad[sl]),
                                                          _ptr(depth[sl]), _ptr(feat_cl), _ptr(pr.point_rank), pr.bn, D, H,
-                                                         W, C, 0 if ctx.feat_cl else 1, 1 if Z == 1 else 0,
+                                                         W, C, 0 if ctx.feat_cl else 1, _column_hint(Z),
                                                          _dtype_code(feat_cl), _stream()),
                            "bevpool_v2_backward_dense")
         fork.join()
-        return depth_grad, feat_grad, None, None, None, None, None
+        return depth_grad, feat_grad, None, None, None, None, None, None
 
 
 class LSSViewTransform(nn.Module):
@@ -310,10 +336,12 @@ class LSSViewTransform(nn.Module):
         return self.voxel_pooling_v2(self.get_geometry(rots, trans), depth, feat)
 
     # -- fused path ---------------------------------------------------------------------------
-    def forward(self, depth, feat, rots, trans, feat_channels_last=False):
+    def forward(self, depth, feat, rots, trans, feat_channels_last=False, s2c=False, memory_format=None):
         """Fused view transform: geometry is never materialised, nothing synchronises with the host.
         depth [B,N,D,fH,fW], feat [B,N,C,fH,fW] ([B,N,fH,fW,C] with feat_channels_last, as `lift` returns it)
-        -> [B,C,Z,Y,X] (all zeros if no point is in range)."""
+        -> [B,C,Z,Y,X] (all zeros if no point is in range), or [B,Z*C,Y,X] = s2c(...) directly with s2c=True.
+        `memory_format=torch.channels_last_3d` returns the same [B,C,Z,Y,X] values as a channels-last view (what a
+        channels-last conv stack consumes) and accepts a channels-last gradient: both layout passes disappear."""
         _check_f32_cuda("rots", rots, (3, 3))
         _check_f32_cuda("trans", trans, (3,))
         B, N = trans.shape[:2]
@@ -327,14 +355,20 @@ class LSSViewTransform(nn.Module):
         if C % 4:
             raise ValueError("the fused path needs C % 4 == 0; use voxel_pooling_v2 for other channel counts")
         groups = self.frame_groups if (self.frame_groups > 1 and B % self.frame_groups == 0) else 1
-        return _FusedViewPool.apply(depth, feat, rots, trans, self, groups, feat_channels_last)
+        if memory_format not in (None, torch.contiguous_format, torch.channels_last_3d):
+            raise ValueError("memory_format must be torch.contiguous_format or torch.channels_last_3d")
+        if memory_format == torch.channels_last_3d:
+            if s2c:
+                raise ValueError("s2c and channels_last_3d are exclusive (s2c of a channels-last grid is not a view)")
+            s2c = "channels_last"
+        return _FusedViewPool.apply(depth, feat, rots, trans, self, groups, feat_channels_last, s2c)
 
-    def lift_splat(self, x, rots, trans, C):
+    def lift_splat(self, x, rots, trans, C, s2c=False):
         """Depthnet output x [B*N, D+C, fH, fW] -> BEV grid [B,C,Z,Y,X]: fused softmax/split/transpose head
         (`lift.get_depth_feat`) feeding the fused view transform. Returns (bev, depth [B*N, D, fH, fW])."""
         from .lift import get_depth_feat
         B, N = trans.shape[:2]
         depth, feat_cl = get_depth_feat(x, self.D, C, channels_last=True)
         bev = self.forward(depth.view(B, N, self.D, self.fH, self.fW), feat_cl.view(B, N, self.fH, self.fW, C), rots, trans,
-                           feat_channels_last=True)
+                           feat_channels_last=True, s2c=s2c)
         return bev, depth

@@ -507,3 +507,56 @@ def test_lift_splat_equals_separate_stages(pkg):
     assert rel_to_max(depth_a.detach().cpu().numpy(), depth_b.detach().cpu().numpy()) <= TOL
     assert rel_to_max(bev_a.detach().cpu().numpy(), bev_b.detach().cpu().numpy()) <= TOL
     assert rel_to_max(xa.grad.cpu().numpy(), xb.grad.cpu().numpy()) <= TOL
+
+
+@pytest.mark.parametrize("cfg_name,B", [("occ_200x200x16_b64", 2), ("bevdet_r50_b8", 2)])
+def test_fused_s2c_layout_is_bit_identical(pkg, cfg_name, B):
+    """§8(f) rank 1: forward(..., s2c=True) writes [B, Z*C, Y, X] directly; it must equal s2c(forward(...)) bit for
+    bit, and so must the gradients (same kernels, same summation order, only the layout pass differs)."""
+    cfg = pkg.synthetic.CONFIGS[cfg_name]
+    view = pkg.LSSViewTransform.from_config(cfg).to(DEV)
+    N, C = cfg.n_cams, cfg.channels
+    rots, trans = pkg.synthetic.camera_ring(B, N, cfg.final_dim, seed=1)
+    rots, trans = rots.to(DEV), trans.to(DEV)
+    torch.manual_seed(2)
+    depth = torch.randn(B, N, view.D, view.fH, view.fW, device=DEV).softmax(2)
+    feat = torch.randn(B, N, C, view.fH, view.fW, device=DEV)
+    X, Y, Z = (int(v) for v in view.nx)
+    g = torch.randn(B, Z * C, Y, X, device=DEV)
+    res = []
+    for s2c in (False, True):
+        d, f = depth.clone().requires_grad_(), feat.clone().requires_grad_()
+        bev = view(d, f, rots, trans, s2c=s2c)
+        if not s2c:
+            bev = view.s2c(bev)
+        assert bev.shape == (B, Z * C, Y, X)
+        bev.backward(g)
+        res.append((bev.detach(), d.grad, f.grad))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("cfg_name,B", [("bevdet_r50_b8", 4), ("occ_200x200x16_b64", 2)])
+def test_fused_channels_last_3d_is_bit_identical(pkg, cfg_name, B):
+    """memory_format=torch.channels_last_3d: same values as the contiguous result (bit for bit), returned as a
+    channels-last view; a channels-last gradient is consumed without a transpose, a contiguous one still works."""
+    cfg = pkg.synthetic.CONFIGS[cfg_name]
+    view = pkg.LSSViewTransform.from_config(cfg, frame_groups=2).to(DEV)
+    N, C = cfg.n_cams, cfg.channels
+    rots, trans = pkg.synthetic.camera_ring(B, N, cfg.final_dim, seed=4)
+    rots, trans = rots.to(DEV), trans.to(DEV)
+    torch.manual_seed(3)
+    depth = torch.randn(B, N, view.D, view.fH, view.fW, device=DEV).softmax(2)
+    feat = torch.randn(B, N, C, view.fH, view.fW, device=DEV)
+    X, Y, Z = (int(v) for v in view.nx)
+    g = torch.randn(B, C, Z, Y, X, device=DEV)
+    d0, f0 = depth.clone().requires_grad_(), feat.clone().requires_grad_()
+    ref = view(d0, f0, rots, trans)
+    ref.backward(g)
+    for g_in in (g.contiguous(memory_format=torch.channels_last_3d), g):
+        d, f = depth.clone().requires_grad_(), feat.clone().requires_grad_()
+        bev = view(d, f, rots, trans, memory_format=torch.channels_last_3d)
+        assert bev.shape == ref.shape and bev.is_contiguous(memory_format=torch.channels_last_3d)
+        assert torch.equal(bev, ref)
+        bev.backward(g_in)
+        assert torch.equal(d.grad, d0.grad) and torch.equal(f.grad, f0.grad)
