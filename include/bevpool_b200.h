@@ -182,6 +182,22 @@ int bevpool_v1_backward(const void* out_grad, const int32_t* geom_feats, const i
                         const int32_t* interval_starts, void* x_grad, int b, int d, int h, int w, int64_t n,
                         int64_t n_intervals, int c, int dtype, void* stream);
 
+/* ------------------------------------------------------------------ sort-free fused view transform (forward)
+ * get_geometry + voxel_pooling_prepare_v2 + bev_pool_v2 forward (cam_stream_lss_bevpoolv2.py:229-258, 294-351,
+ * 260-292) as ONE pixel-major pass: ranks are computed per camera pixel block (and written to point_rank
+ * [B*N*D*H*W] for bevpool_v2_backward_dense), depth-weighted feature rows are accumulated per run of points
+ * sharing a voxel and pushed into an fp32 grid with vector REDs; no sort, no ranks_* arrays. The summation order
+ * across image columns is therefore not fixed (see csrc/pool_scatter.cu); the sorted entry points above are the
+ * deterministic alternative. feat is channels-last [B*N, H, W, C], C % 4 == 0, C <= 128.
+ * from_geometry == 0: point_rank is an INPUT (e.g. from bevpool_prepare_v2) and frustum/rots/trans are unused.
+ * Output layouts as bevpool_v2_forward_dense (n_frames x rows_per_frame x X voxels; s2c = (B*Z, Y)).
+ * scratch: bevpool_view_forward_scratch_bytes() bytes, 16-byte aligned (0 for fp32 channels-last output). */
+size_t bevpool_view_forward_scratch_bytes(int64_t n_voxels, int c, int layout, int dtype);
+int bevpool_view_forward(const void* depth, const void* feat, const float* frustum, const float* rots,
+                         const float* trans, const bevpool_grid_t* g, int c, int32_t* point_rank, int from_geometry,
+                         void* out, int64_t n_frames, int64_t rows_per_frame, int layout, int dtype, void* scratch,
+                         size_t scratch_bytes, void* stream);
+
 /* ------------------------------------------------------------------ lift head
  * CamEncode.get_depth_feat (cam_stream_lss_bevpoolv2.py:134-141) fused with the NCHW->NHWC transpose of the
  * context features (:282): x [BN, D+C, H, W] -> depth [BN, D, H, W] = softmax over the first D channels and

@@ -1,0 +1,354 @@
+// Sort-free fused view transform, forward direction (the default path of LSSViewTransform.forward):
+//
+//   memset(acc)                          fp32 accumulation grid [V][C], channels-last
+//   view_fwd_scatter_kernel              geometry -> voxel rank (written to point_rank for the backward) ->
+//                                        depth-weighted feature sums pushed into the grid with 128-bit REDs
+//   acc_layout_kernel / acc_convert      [V][C] fp32 -> [B,C,Z,Y,X] (or s2c / channels-last) in the io dtype
+//
+// Why: in the sorted formulation (pool_dense.cu) every kept point gathers its C-channel feature row from L2
+// (P*C*e bytes, 353 MB per step at cfg 2 — the forward's actual bound) and the voxel order has to be produced by
+// a multi-pass radix sort first. Walking the frustum PIXEL-major instead keeps the feature rows of a pixel
+// column in registers for all D bins; what leaves the SM is one row per RUN of consecutive points that share a
+// voxel (all H rows of an image column at one depth bin usually do, SURVEY.md §8(d): mean interval = 15 points),
+// i.e. ~P/10 rows of RED traffic, and no sort, no interval table, no ranks_* arrays exist at all.
+//
+// Price: contributions of different image columns / cameras to one voxel meet in L2 atomics, so the fp32
+// summation ORDER across them is not fixed (voxels fed by one or two runs — the majority — are still
+// bit-reproducible). torch.use_deterministic_algorithms(True) or LSSViewTransform(deterministic=True) selects
+// the sorted path instead; both are inside the 1e-5 parity bar against the float64 oracle.
+//
+// Block shape and staging are those of the joint backward (pool_dense.cu): a CTA owns 8(w) x 4(h) pixels of
+// one camera image, warp = image column, ranks and depths staged as [d][8] int4/float4 so one broadcast LDS.128
+// yields the 4 rows of a bin. Each warp keeps FOUR open accumulators keyed by voxel rank (a 4-entry fully
+// associative cache, all comparisons warp-uniform): a point joins the accumulator that already holds its
+// voxel, otherwise it evicts (REDs out) the accumulator of its own row.
+#include "common.cuh"
+
+namespace bevpool {
+
+constexpr int kScW = 8, kScH = 4, kScPix = kScW * kScH;
+constexpr int kScWarps = 8, kScThreads = kScWarps * 32;
+
+struct ScatterParams {
+  int c, d, h, w;
+  int bn, n_cams;
+  int blocks_w, blocks_h;
+  int nx, ny, nz;
+  float lo[3], dx[3];
+  int from_geometry;   // 1: compute ranks from frustum/rots/trans and write point_rank; 0: read point_rank
+};
+
+__device__ __forceinline__ void red_add_f32x4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ float4 mul4(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+
+template <typename T, int CH4>
+__global__ void __launch_bounds__(kScThreads, 3)
+view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat, const float* __restrict__ frustum,
+                        const float* __restrict__ rots, const float* __restrict__ trans, ScatterParams prm,
+                        int* __restrict__ point_rank, float* __restrict__ acc_grid) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int4* s_rank4 = reinterpret_cast<int4*>(smem_raw);                               // [d][8]: ranks of rows h0..h0+3
+  float4* s_depth4 = reinterpret_cast<float4*>(s_rank4 + (size_t)prm.d * kScW);    // [d][8]
+  __shared__ float s_cam[12];
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int c4 = CH4 ? CH4 : (prm.c >> 2);
+  const int C = 4 * c4;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const int blk = blockIdx.x;
+  const int per_img = prm.blocks_w * prm.blocks_h;
+  const int bn = blk / per_img;
+  const int brem = blk - bn * per_img;
+  const int bh = brem / prm.blocks_w, bw = brem - bh * prm.blocks_w;
+  const int h0 = bh * kScH, w0 = bw * kScW;
+  const int hw = prm.h * prm.w;
+  const int64_t img_base = (int64_t)bn * prm.d * hw;
+  pdl_wait();
+  if (prm.from_geometry) {
+    if (threadIdx.x < 12)
+      s_cam[threadIdx.x] = threadIdx.x < 9 ? __ldg(rots + bn * 9 + threadIdx.x) : __ldg(trans + bn * 3 + threadIdx.x - 9);
+    __syncthreads();
+  }
+  // ---- stage ranks / depths of the block: 8 consecutive w = one 32-byte sector per (d, h)
+  {
+    const int hl = lane >> 3, wl = lane & 7;
+    const bool in = h0 + hl < prm.h && w0 + wl < prm.w;
+    const int pix = (h0 + hl) * prm.w + w0 + wl;
+    const int64_t vpf = (int64_t)prm.nx * prm.ny * prm.nz;
+    const int64_t frame_base = (int64_t)(bn / prm.n_cams) * vpf;
+    for (int d0 = 0; d0 < prm.d; d0 += 4 * kScWarps) {
+      int r[4];
+      float dv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int dd = d0 + k * kScWarps + warp;
+        r[k] = -1;
+        dv[k] = 0.f;
+        if (in && dd < prm.d) {
+          const int64_t o = (int64_t)dd * hw + pix;
+          dv[k] = Vec4<T>::load1(depth, img_base + o);
+          if (prm.from_geometry) {
+            float x, y, z;
+            cam_point(frustum, s_cam, o, x, y, z);
+            int vx, vy, vz;
+            const bool ok = voxel_index(x, prm.lo[0], prm.dx[0], prm.nx, vx) & voxel_index(y, prm.lo[1], prm.dx[1], prm.ny, vy) &
+                            voxel_index(z, prm.lo[2], prm.dx[2], prm.nz, vz);
+            if (ok) r[k] = (int)(frame_base + ((int64_t)vz * prm.ny + vy) * prm.nx + vx);
+            point_rank[img_base + o] = r[k];
+          } else {
+            r[k] = ldg_stream_i32(point_rank + img_base + o);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int dd = d0 + k * kScWarps + warp;
+        if (dd < prm.d) {
+          reinterpret_cast<int*>(s_rank4 + dd * kScW + wl)[hl] = r[k];
+          reinterpret_cast<float*>(s_depth4 + dd * kScW + wl)[hl] = r[k] >= 0 ? dv[k] : 0.f;   // dropped: weight 0
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  const int ww = w0 + warp;   // this warp's image column
+  if (ww >= prm.w) return;    // warp-uniform; no barrier below
+  const bool act = lane < c4;
+  const int lane_c = 4 * (act ? lane : c4 - 1);   // idle lanes alias the last chunk; they never issue a RED
+  float4 fv[kScH], acc[kScH];
+  int cur[kScH];
+#pragma unroll
+  for (int p = 0; p < kScH; ++p) {
+    acc[p] = zero;
+    cur[p] = -1;
+    fv[p] = (h0 + p < prm.h) ? Vec4<T>::load(feat, ((int64_t)bn * hw + (h0 + p) * prm.w + ww) * C + lane_c) : zero;
+  }
+  float* grid_lane = acc_grid + lane_c;
+  const int4* rank_col = s_rank4 + warp;
+  const float4* depth_col = s_depth4 + warp;
+
+  // point (row p, rank rp, depth dp): join the accumulator holding voxel rp, else evict row p's accumulator
+#define BEVPOOL_SC_PUT(p, rp, dp)                                                        \
+  if ((rp) >= 0) {                                                                       \
+    if ((rp) == cur[0]) acc[0] = fma4(fv[p], (dp), acc[0]);                              \
+    else if ((rp) == cur[1]) acc[1] = fma4(fv[p], (dp), acc[1]);                         \
+    else if ((rp) == cur[2]) acc[2] = fma4(fv[p], (dp), acc[2]);                         \
+    else if ((rp) == cur[3]) acc[3] = fma4(fv[p], (dp), acc[3]);                         \
+    else {                                                                               \
+      if (cur[p] >= 0 && act) red_add_f32x4(grid_lane + (int64_t)cur[p] * C, acc[p]);    \
+      cur[p] = (rp);                                                                     \
+      acc[p] = mul4(fv[p], (dp));                                                        \
+    }                                                                                    \
+  }
+
+  for (int d0 = 0; d0 < prm.d; d0 += 4) {
+    int4 r[4];
+    float4 dp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int dd = min(d0 + u, prm.d - 1);
+      r[u] = rank_col[dd * kScW];        // broadcast LDS.128
+      dp[u] = depth_col[dd * kScW];
+      if (d0 + u >= prm.d) r[u] = make_int4(-1, -1, -1, -1);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int lead = max(max(r[u].x, r[u].y), max(r[u].z, r[u].w));
+      if (lead < 0) continue;   // warp-uniform: nothing kept in this bin
+      // fast path (every bin of a Z == 1 grid, most bins otherwise): all kept rows of the column share ONE voxel.
+      // One comparison against the open accumulator, then four unconditional FMAs (dropped rows weigh 0).
+      const bool shared = (r[u].x < 0 || r[u].x == lead) && (r[u].y < 0 || r[u].y == lead) &&
+                          (r[u].z < 0 || r[u].z == lead) && (r[u].w < 0 || r[u].w == lead);
+      if (shared) {
+        if (lead != cur[0]) {
+          if (cur[0] >= 0 && act) red_add_f32x4(grid_lane + (int64_t)cur[0] * C, acc[0]);
+          cur[0] = lead;
+          acc[0] = zero;
+        }
+        acc[0] = fma4(fv[0], dp[u].x, acc[0]);
+        acc[0] = fma4(fv[1], dp[u].y, acc[0]);
+        acc[0] = fma4(fv[2], dp[u].z, acc[0]);
+        acc[0] = fma4(fv[3], dp[u].w, acc[0]);
+        continue;
+      }
+      BEVPOOL_SC_PUT(0, r[u].x, dp[u].x)
+      BEVPOOL_SC_PUT(1, r[u].y, dp[u].y)
+      BEVPOOL_SC_PUT(2, r[u].z, dp[u].z)
+      BEVPOOL_SC_PUT(3, r[u].w, dp[u].w)
+    }
+  }
+#undef BEVPOOL_SC_PUT
+  if (act) {
+#pragma unroll
+    for (int p = 0; p < kScH; ++p)
+      if (cur[p] >= 0) red_add_f32x4(grid_lane + (int64_t)cur[p] * C, acc[p]);
+  }
+}
+
+// fp32 [F][V][C] -> T [F][C][V]; a CTA moves all channels of 64 consecutive voxels, 128-bit on both sides.
+constexpr int kAlCols = 64;
+template <typename T>
+__global__ void __launch_bounds__(256)
+acc_layout_kernel(const float* __restrict__ src_cl, T* __restrict__ dst, int c, int64_t vpf, int64_t tiles_per_frame) {
+  extern __shared__ float t[];            // [c][kAlCols + 1]
+  pdl_wait();
+  const int64_t b = blockIdx.x / tiles_per_frame;
+  const int64_t v0 = (blockIdx.x % tiles_per_frame) * kAlCols;
+  const int ncol = (int)min((int64_t)kAlCols, vpf - v0);
+  const int64_t rank0 = b * vpf + v0;
+  const int c4 = c >> 2;
+  for (int i = threadIdx.x; i < ncol * c4; i += 256) {
+    const int col = i / c4, q = i - col * c4;
+    const float4 v = Vec4<float>::load_stream(src_cl, (rank0 + col) * c + 4 * q);
+    float* o = t + (4 * q) * (kAlCols + 1) + col;
+    o[0] = v.x; o[kAlCols + 1] = v.y; o[2 * (kAlCols + 1)] = v.z; o[3 * (kAlCols + 1)] = v.w;
+  }
+  __syncthreads();
+  T* d = dst + (b * c) * vpf + v0;
+  const bool vec = ncol == kAlCols && (vpf & 3) == 0 && ((((uintptr_t)dst) & 15) == 0);
+  if (vec) {
+    for (int i = threadIdx.x; i < c * (kAlCols / 4); i += 256) {
+      const int ch = i / (kAlCols / 4), q = i % (kAlCols / 4);
+      const float* p = t + ch * (kAlCols + 1) + 4 * q;
+      Vec4<T>::store(d, (int64_t)ch * vpf + 4 * q, make_float4(p[0], p[1], p[2], p[3]));
+    }
+  } else {
+    for (int i = threadIdx.x; i < c * kAlCols; i += 256) {
+      const int ch = i / kAlCols, q = i % kAlCols;
+      if (q < ncol) Vec4<T>::store1s(d, (int64_t)ch * vpf + q, t[ch * (kAlCols + 1) + q]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+acc_convert_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n4) {
+  pdl_wait();
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256)
+    Vec4<T>::store(dst, 4 * i, Vec4<float>::load_stream(src, 4 * i));
+}
+
+template <typename T, int CH4>
+static void scatter_launch(const void* depth, const void* feat, const float* frustum, const float* rots, const float* trans,
+                           const ScatterParams& prm, int32_t* point_rank, float* acc, unsigned blocks, size_t smem,
+                           cudaStream_t st) {
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaFuncSetAttribute(view_fwd_scatter_kernel<T, CH4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  launch_pdl(view_fwd_scatter_kernel<T, CH4>, dim3(blocks), dim3(kScThreads), smem, st, (const T*)depth, (const T*)feat, frustum,
+             rots, trans, prm, point_rank, acc);
+}
+
+template <typename T>
+static int view_forward_t(const void* depth, const void* feat, const float* frustum, const float* rots, const float* trans,
+                          ScatterParams prm, int32_t* point_rank, void* out, int64_t n_frames, int64_t rows_per_frame,
+                          int layout, void* scratch, cudaStream_t st) {
+  const int64_t n_vox = (int64_t)(prm.bn / prm.n_cams) * prm.nx * prm.ny * prm.nz;
+  const bool direct = layout == BEVPOOL_LAYOUT_BZYXC && sizeof(T) == 4;   // REDs land in the caller's tensor
+  float* acc = direct ? (float*)out : (float*)scratch;
+  cudaMemsetAsync(acc, 0, (size_t)n_vox * prm.c * sizeof(float), st);
+  prm.blocks_w = (prm.w + kScW - 1) / kScW;
+  prm.blocks_h = (prm.h + kScH - 1) / kScH;
+  const int64_t blocks = (int64_t)prm.bn * prm.blocks_w * prm.blocks_h;
+  if (blocks > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
+  const size_t smem = (size_t)prm.d * kScW * (sizeof(int4) + sizeof(float4));
+  if (smem > 200 * 1024) return BEVPOOL_ERR_BAD_ARG;
+  if (blocks > 0) {
+    switch (prm.c) {
+      case 32: scatter_launch<T, 8>(depth, feat, frustum, rots, trans, prm, point_rank, acc, (unsigned)blocks, smem, st); break;
+      case 64: scatter_launch<T, 16>(depth, feat, frustum, rots, trans, prm, point_rank, acc, (unsigned)blocks, smem, st); break;
+      case 80: scatter_launch<T, 20>(depth, feat, frustum, rots, trans, prm, point_rank, acc, (unsigned)blocks, smem, st); break;
+      case 128: scatter_launch<T, 32>(depth, feat, frustum, rots, trans, prm, point_rank, acc, (unsigned)blocks, smem, st); break;
+      default: scatter_launch<T, 0>(depth, feat, frustum, rots, trans, prm, point_rank, acc, (unsigned)blocks, smem, st); break;
+    }
+    count_launch();
+  }
+  if (direct) return launch_status();
+  if (layout == BEVPOOL_LAYOUT_BZYXC) {
+    const int64_t n4 = n_vox * prm.c / 4;
+    int64_t blocks_c = (n4 + 255) / 256;
+    if (blocks_c > (int64_t)kNumSMs * 16) blocks_c = (int64_t)kNumSMs * 16;
+    if (blocks_c > 0) {
+      launch_pdl(acc_convert_kernel<T>, dim3((unsigned)blocks_c), dim3(256), 0, st, (const float*)acc, (T*)out, n4);
+      count_launch();
+    }
+    return launch_status();
+  }
+  const int64_t vpf = rows_per_frame * prm.nx;
+  const int64_t tiles_per_frame = (vpf + kAlCols - 1) / kAlCols;
+  const int64_t total = tiles_per_frame * n_frames;
+  if (total > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
+  if (total > 0) {
+    const size_t sm = sizeof(float) * (size_t)prm.c * (kAlCols + 1);
+    static size_t attr = 0;
+    if (sm > 48 * 1024 && sm > attr) {
+      cudaFuncSetAttribute(acc_layout_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      attr = sm;
+    }
+    launch_pdl(acc_layout_kernel<T>, dim3((unsigned)total), dim3(256), sm, st, (const float*)acc, (T*)out, prm.c, vpf,
+               tiles_per_frame);
+    count_launch();
+  }
+  return launch_status();
+}
+
+}  // namespace bevpool
+
+using namespace bevpool;
+
+extern "C" size_t bevpool_view_forward_scratch_bytes(int64_t n_voxels, int c, int layout, int dtype) {
+  if (n_voxels < 0 || c <= 0) return 0;
+  if (layout == BEVPOOL_LAYOUT_BZYXC && dtype == BEVPOOL_F32) return 0;
+  return (size_t)n_voxels * c * sizeof(float);
+}
+
+extern "C" int bevpool_view_forward(const void* depth, const void* feat, const float* frustum, const float* rots,
+                                    const float* trans, const bevpool_grid_t* g, int c, int32_t* point_rank,
+                                    int from_geometry, void* out, int64_t n_frames, int64_t rows_per_frame, int layout,
+                                    int dtype, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!g || g->b < 0 || g->n <= 0 || g->d <= 0 || g->h < 0 || g->w < 0) return BEVPOOL_ERR_BAD_ARG;
+  if (g->nx[0] <= 0 || g->nx[1] <= 0 || g->nx[2] <= 0) return BEVPOOL_ERR_BAD_ARG;
+  if (c <= 0 || c % 4 || c > 128) return BEVPOOL_ERR_BAD_CHANNELS;
+  if (layout != BEVPOOL_LAYOUT_BZYXC && layout != BEVPOOL_LAYOUT_BCZYX) return BEVPOOL_ERR_BAD_ARG;
+  if (dtype != BEVPOOL_F32 && dtype != BEVPOOL_BF16) return BEVPOOL_ERR_BAD_ARG;
+  const int64_t n_vox = (int64_t)g->b * g->nx[0] * g->nx[1] * g->nx[2];
+  const int64_t p0 = (int64_t)g->b * g->n * g->d * g->h * g->w;
+  if (n_vox >= INT32_MAX || p0 >= INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
+  if (layout == BEVPOOL_LAYOUT_BCZYX && n_frames * rows_per_frame * g->nx[0] != n_vox) return BEVPOOL_ERR_BAD_ARG;
+  if (n_vox == 0) return BEVPOOL_OK;
+  if (!out || !point_rank) return BEVPOOL_ERR_BAD_ARG;
+  if (p0 > 0 && (!depth || !feat)) return BEVPOOL_ERR_BAD_ARG;
+  if (from_geometry && p0 > 0 && (!frustum || !rots || !trans)) return BEVPOOL_ERR_BAD_ARG;
+  if ((uintptr_t)feat % 16 || (uintptr_t)out % 16 || (uintptr_t)scratch % 16) return BEVPOOL_ERR_BAD_ARG;
+  if (scratch_bytes < bevpool_view_forward_scratch_bytes(n_vox, c, layout, dtype)) return BEVPOOL_ERR_WORKSPACE;
+  if (scratch_bytes && !scratch) return BEVPOOL_ERR_BAD_ARG;
+  ScatterParams prm;
+  prm.c = c;
+  prm.d = g->d;
+  prm.h = g->h;
+  prm.w = g->w;
+  prm.bn = g->b * g->n;
+  prm.n_cams = g->n;
+  prm.nx = g->nx[0];
+  prm.ny = g->nx[1];
+  prm.nz = g->nx[2];
+  for (int a = 0; a < 3; ++a) {
+    prm.lo[a] = g->lo[a];
+    prm.dx[a] = g->dx[a];
+  }
+  prm.from_geometry = from_geometry ? 1 : 0;
+  prm.blocks_w = prm.blocks_h = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == BEVPOOL_F32)
+    return view_forward_t<float>(depth, feat, frustum, rots, trans, prm, point_rank, out, n_frames, rows_per_frame, layout,
+                                 scratch, st);
+  return view_forward_t<__nv_bfloat16>(depth, feat, frustum, rots, trans, prm, point_rank, out, n_frames, rows_per_frame,
+                                       layout, scratch, st);
+}

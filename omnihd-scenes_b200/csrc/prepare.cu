@@ -103,15 +103,6 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 }
 
 // ------------------------------------------------------------------------------------------ geometry
-__device__ __forceinline__ void cam_point(const float* __restrict__ frustum, const float* cam /*R[9] t[3]*/,
-                                          int64_t dhw, float& x, float& y, float& z) {
-  const float u = __ldg(frustum + 3 * dhw + 0), v = __ldg(frustum + 3 * dhw + 1), dd = __ldg(frustum + 3 * dhw + 2);
-  const float px = __fmul_rn(u, dd), py = __fmul_rn(v, dd), pz = dd;
-  x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cam[0], px), __fmul_rn(cam[1], py)), __fmul_rn(cam[2], pz)), cam[9]);
-  y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cam[3], px), __fmul_rn(cam[4], py)), __fmul_rn(cam[5], pz)), cam[10]);
-  z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cam[6], px), __fmul_rn(cam[7], py)), __fmul_rn(cam[8], pz)), cam[11]);
-}
-
 // grid: (ceil(DHW / 256), BN): every CTA works inside one camera, so R|t are CTA-uniform
 __global__ void __launch_bounds__(256)
 geometry_kernel(const float* __restrict__ frustum, const float* __restrict__ rots, const float* __restrict__ trans,
@@ -143,15 +134,6 @@ struct GridDev {
   int nx, ny, nz;
   float lo[3], dx[3];
 };
-
-__device__ __forceinline__ bool voxel_index(float c, float lo, float dx, int n, int& v) {
-  const float q = __fdiv_rn(__fsub_rn(c, lo), dx);
-  // .long(): truncation toward zero; NaN / beyond int64 come out as INT64_MIN on the CPU -> dropped
-  if (!(fabsf(q) < 9.0e18f)) return false;
-  const long long t = (long long)q;
-  v = (int)t;
-  return t >= 0 && t < n;
-}
 
 // One CTA = one sort tile of the (uncompacted) point list: rank of every point, the tile's pass-0
 // digit histogram (tile_hist0[tile][bins0]), digit totals of all passes, kept count.

@@ -131,6 +131,28 @@ def _prepare_device(coor, frustum, rots, trans, B, N, D, H, W, dx, bx, nx, devic
     return out
 
 
+def _view_forward_scatter(depth, feat_cl, out, view, rots, trans, n, N, D, H, W, C, frames, rows, layout):
+    """Sort-free forward (csrc/pool_scatter.cu) of `n` frames; returns the _Prepared stub the backward needs."""
+    import ctypes
+    lib = _lib.load()
+    g = _grid_struct(n, N, D, H, W, view.dx, view.bx, view.nx)
+    p0 = n * N * D * H * W
+    vtot = n * g.nx[0] * g.nx[1] * g.nx[2]
+    if p0 >= 2 ** 31 - 1 or vtot >= 2 ** 31 - 1:
+        raise ValueError("problem too large for int32 ranks: shard the frame batch")
+    pr = _Prepared()
+    pr.rb = pr.rd = pr.rf = pr.starts = pr.lengths = pr.counts = None
+    pr.point_rank = torch.empty(max(p0, 1), dtype=torch.int32, device=out.device)
+    pr.bn, pr.d, pr.h, pr.w, pr.hw, pr.p0 = n * N, D, H, W, H * W, p0
+    code = _dtype_code(feat_cl)
+    nbytes = lib.bevpool_view_forward_scratch_bytes(vtot, C, layout, code)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=out.device) if nbytes else None
+    _lib.check(lib.bevpool_view_forward(_ptr(depth), _ptr(feat_cl), _ptr(view.frustum), _ptr(rots), _ptr(trans),
+                                        ctypes.byref(g), C, _ptr(pr.point_rank), 1, _ptr(out), frames, rows, layout, code,
+                                        _ptr(scratch), nbytes, _stream()), "bevpool_view_forward")
+    return pr
+
+
 def voxel_pooling_prepare_v2(coor, dx, bx, nx):
     """Free-function form of `LiftSplatShoot.voxel_pooling_prepare_v2(self, coor)`.
 
@@ -223,21 +245,27 @@ class _FusedViewPool(torch.autograd.Function):
         planes, rows = (Z, Y) if s2c else (1, Z * Y)
         n = B // groups
         saved = []
+        # sorted (deterministic summation order, radix sort + streaming pool) or sort-free scatter (default)
+        sorted_path = view.deterministic or torch.are_deterministic_algorithms_enabled() or C > 128
         fork = _Fork(feat.device, groups)
         for g, st in enumerate(fork.streams):
             sl = slice(g * n, (g + 1) * n)
             with torch.cuda.stream(st):
-                pr = _prepare_device(None, view.frustum, rots[sl], trans[sl], n, N, D, H, W, view.dx, view.bx, view.nx,
-                                     feat.device, want_intervals=False)
                 if feat_channels_last:                                                # lift head already wrote NHWC
                     feat_cl = feat[sl]
                 else:
-                    feat_cl = feat.new_empty((pr.bn, H, W, C))
-                    _launch_transpose(feat[sl], feat_cl, pr.bn, C, pr.hw, True)       # [BN,C,HW] -> [BN,HW,C]
-                vox_pt = _launch_voxel_table(pr.rb, pr.p0, pr.counts, n * Z * Y * X)
-                _launch_forward_dense(depth[sl], feat_cl, out[sl], pr.rd, None, pr.rb, vox_pt, n * planes, rows, X,
-                                      _lib.LAYOUT_BZYXC if cl_out else _lib.LAYOUT_BCZYX, dhw=D * pr.hw, hw=pr.hw,
-                                      n_points=pr.p0, counts_dev=pr.counts)
+                    feat_cl = feat.new_empty((n * N, H, W, C))
+                    _launch_transpose(feat[sl], feat_cl, n * N, C, H * W, True)       # [BN,C,HW] -> [BN,HW,C]
+                layout = _lib.LAYOUT_BZYXC if cl_out else _lib.LAYOUT_BCZYX
+                if sorted_path:
+                    pr = _prepare_device(None, view.frustum, rots[sl], trans[sl], n, N, D, H, W, view.dx, view.bx,
+                                         view.nx, feat.device, want_intervals=False)
+                    vox_pt = _launch_voxel_table(pr.rb, pr.p0, pr.counts, n * Z * Y * X)
+                    _launch_forward_dense(depth[sl], feat_cl, out[sl], pr.rd, None, pr.rb, vox_pt, n * planes, rows, X,
+                                          layout, dhw=D * pr.hw, hw=pr.hw, n_points=pr.p0, counts_dev=pr.counts)
+                else:
+                    pr = _view_forward_scatter(depth[sl], feat_cl, out[sl], view, rots[sl], trans[sl], n, N, D, H, W, C,
+                                               n * planes, rows, layout)
             saved.append((pr, feat_cl))
         fork.join()
         ctx.saved, ctx.dims, ctx.groups, ctx.feat_cl, ctx.s2c = saved, (B, N, C, D, H, W, X, Y, Z), groups, feat_channels_last, s2c
@@ -283,9 +311,12 @@ class LSSViewTransform(nn.Module):
     same attribute names (`dx`, `bx`, `nx`, `frustum`, `D`, `fH`, `fW`) and method names, no conv nets.
     Per-axis bounds are accepted (the reference forces one scalar `grid` for x, y and z, :164-169)."""
 
-    def __init__(self, final_dim, downsample, dbound, xbound, ybound, zbound, frame_groups=1):
+    def __init__(self, final_dim, downsample, dbound, xbound, ybound, zbound, frame_groups=1, deterministic=False):
         super().__init__()
         self.frame_groups = frame_groups          # fused path: independent frame groups on concurrent streams
+        # fused path: False = sort-free pixel-major forward (fp32 sums meet in L2 atomics: order across image
+        # columns not fixed); True (or torch.use_deterministic_algorithms(True)) = sorted, fixed-order forward
+        self.deterministic = deterministic
         self.final_dim = tuple(final_dim)
         self.downsample = downsample
         self.grid_conf = dict(xbound=list(xbound), ybound=list(ybound), zbound=list(zbound), dbound=list(dbound))
@@ -295,8 +326,9 @@ class LSSViewTransform(nn.Module):
         self.D = self.frustum.shape[0]
 
     @classmethod
-    def from_config(cls, cfg, frame_groups=1):
-        return cls(cfg.final_dim, cfg.downsample, cfg.dbound, cfg.xbound, cfg.ybound, cfg.zbound, frame_groups)
+    def from_config(cls, cfg, frame_groups=1, deterministic=False):
+        return cls(cfg.final_dim, cfg.downsample, cfg.dbound, cfg.xbound, cfg.ybound, cfg.zbound, frame_groups,
+                   deterministic)
 
     @classmethod
     def from_lss_args(cls, final_dim, camera_depth_range, pc_range, downsample, grid):

@@ -21,9 +21,39 @@ for s in range(NS):
     rots, trans = pkg.synthetic.camera_ring(B, N, cfg.final_dim, seed=s)
     depth, feat, gout = pkg.synthetic.pool_inputs(cfg, batch=B, seed=s)
     sets.append(dict(rots=rots.to(dev), trans=trans.to(dev), depth=depth.to(dev, dt), feat=feat.to(dev, dt), gout=gout.to(dev, dt)))
-stages = ["prepare", "feat_transpose", "voxel_table", "pool_fwd", "og_transpose", "pool_bwd"]
+SCATTER = os.environ.get("PATH_KIND", "scatter") == "scatter"      # PATH_KIND=sorted: radix sort + streaming forward
+stages = (["feat_transpose", "scatter_fwd(memset+kernel)", "acc_layout", "og_transpose", "pool_bwd"] if SCATTER else
+          ["prepare", "feat_transpose", "voxel_table", "pool_fwd", "og_transpose", "pool_bwd"])
+import ctypes
+
+
+def run_scatter(s, upto):
+    st = torch.cuda.current_stream().cuda_stream
+    fcl = s["feat"].new_empty((B * N, H, W, C)); bp._launch_transpose(s["feat"], fcl, B * N, C, H * W, True)
+    if upto == 0: return fcl
+    g = vt._grid_struct(B, N, D, H, W, view.dx, view.bx, view.nx)
+    prk = torch.empty(B * N * D * H * W, dtype=torch.int32, device=dev)
+    acc = torch.empty((B, Z, Y, X, C), dtype=torch.float32, device=dev)
+    code = bp._dtype_code(fcl)
+    if upto == 1 and dt == torch.float32:      # kernel + memset only: channels-last fp32 output, no layout pass
+        lib.bevpool_view_forward(s["depth"].data_ptr(), fcl.data_ptr(), view.frustum.data_ptr(), s["rots"].data_ptr(), s["trans"].data_ptr(),
+                                 ctypes.byref(g), C, prk.data_ptr(), 1, acc.data_ptr(), B, Z * Y, 0, code, None, 0, st)
+        return acc, prk
+    out = s["feat"].new_empty((B, C, Z, Y, X))
+    lib.bevpool_view_forward(s["depth"].data_ptr(), fcl.data_ptr(), view.frustum.data_ptr(), s["rots"].data_ptr(), s["trans"].data_ptr(),
+                             ctypes.byref(g), C, prk.data_ptr(), 1, out.data_ptr(), B, Z * Y, 1, code, acc.data_ptr(), acc.numel() * 4, st)
+    if upto <= 2: return out, prk, acc
+    og = s["gout"].new_empty((B, Z, Y, X, C)); bp._launch_transpose(s["gout"], og, B, C, Z * Y * X, True)
+    if upto == 3: return og
+    dg = torch.empty_like(s["depth"]); fg = torch.empty_like(s["feat"])
+    lib.bevpool_v2_backward_dense(og.data_ptr(), dg.data_ptr(), fg.data_ptr(), s["depth"].data_ptr(), fcl.data_ptr(), prk.data_ptr(),
+                                  B * N, D, H, W, C, 1, int(os.environ.get('HINT', 1 if Z == 1 else 0)), code, st)
+    return (out, dg, fg, acc, prk)
+
 
 def run(s, upto):
+    if SCATTER:
+        return run_scatter(s, upto)
     st = torch.cuda.current_stream().cuda_stream
     pr = vt._prepare_device(None, view.frustum, s["rots"], s["trans"], B, N, D, H, W, view.dx, view.bx, view.nx, dev, want_intervals=False)
     if upto == 0: return pr

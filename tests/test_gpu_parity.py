@@ -322,14 +322,15 @@ def test_view_transform_fwd_bwd_vs_oracle(pkg, orc, cfg_name, B):
     gd, gf = orc.bev_pool_v2_backward(gout.permute(0, 2, 3, 4, 1).contiguous().numpy(), depth.numpy(), feat_cl,
                                       rd, rf, rb, exact=True)
     view = view.to(DEV)
-    for mode in ("api", "fused", "fused_groups"):
+    for mode in ("api", "fused", "fused_groups", "fused_sorted", "fused_sorted_groups"):
         d = depth.to(DEV).requires_grad_()
         f = feat.to(DEV).requires_grad_()
         view.frame_groups = 1
+        view.deterministic = "sorted" in mode      # default: sort-free scatter forward; True: sorted streaming forward
         if mode == "api":
             bev = view.voxel_pooling_v2(view.get_geometry(rots.to(DEV), trans.to(DEV)), d, f)
         else:
-            if mode == "fused_groups":      # independent frame groups on concurrent streams
+            if mode.endswith("groups"):      # independent frame groups on concurrent streams
                 view.frame_groups = 2 if B % 2 == 0 else 1
             bev = view(d, f, rots.to(DEV), trans.to(DEV))
         assert bev.shape == (B, C, Z, Y, X)
@@ -523,17 +524,22 @@ def test_fused_s2c_layout_is_bit_identical(pkg, cfg_name, B):
     feat = torch.randn(B, N, C, view.fH, view.fW, device=DEV)
     X, Y, Z = (int(v) for v in view.nx)
     g = torch.randn(B, Z * C, Y, X, device=DEV)
-    res = []
-    for s2c in (False, True):
-        d, f = depth.clone().requires_grad_(), feat.clone().requires_grad_()
-        bev = view(d, f, rots, trans, s2c=s2c)
-        if not s2c:
-            bev = view.s2c(bev)
-        assert bev.shape == (B, Z * C, Y, X)
-        bev.backward(g)
-        res.append((bev.detach(), d.grad, f.grad))
-    for a, b in zip(*res):
-        assert torch.equal(a, b)
+    for det in (True, False):
+        view.deterministic = det
+        res = []
+        for s2c in (False, True):
+            d, f = depth.clone().requires_grad_(), feat.clone().requires_grad_()
+            bev = view(d, f, rots, trans, s2c=s2c)
+            if not s2c:
+                bev = view.s2c(bev)
+            assert bev.shape == (B, Z * C, Y, X)
+            bev.backward(g)
+            res.append((bev.detach(), d.grad, f.grad))
+        for a, b in zip(*res):
+            if det:
+                assert torch.equal(a, b)
+            else:   # sort-free forward: summation order across image columns is not fixed; backward is exact
+                assert rel_to_max(a.cpu().numpy(), b.cpu().numpy()) <= TOL
 
 
 @pytest.mark.parametrize("cfg_name,B", [("bevdet_r50_b8", 4), ("occ_200x200x16_b64", 2)])
@@ -550,13 +556,53 @@ def test_fused_channels_last_3d_is_bit_identical(pkg, cfg_name, B):
     feat = torch.randn(B, N, C, view.fH, view.fW, device=DEV)
     X, Y, Z = (int(v) for v in view.nx)
     g = torch.randn(B, C, Z, Y, X, device=DEV)
-    d0, f0 = depth.clone().requires_grad_(), feat.clone().requires_grad_()
-    ref = view(d0, f0, rots, trans)
-    ref.backward(g)
-    for g_in in (g.contiguous(memory_format=torch.channels_last_3d), g):
-        d, f = depth.clone().requires_grad_(), feat.clone().requires_grad_()
-        bev = view(d, f, rots, trans, memory_format=torch.channels_last_3d)
-        assert bev.shape == ref.shape and bev.is_contiguous(memory_format=torch.channels_last_3d)
-        assert torch.equal(bev, ref)
-        bev.backward(g_in)
-        assert torch.equal(d.grad, d0.grad) and torch.equal(f.grad, f0.grad)
+    for det in (True, False):
+        view.deterministic = det
+        d0, f0 = depth.clone().requires_grad_(), feat.clone().requires_grad_()
+        ref = view(d0, f0, rots, trans)
+        ref.backward(g)
+        for g_in in (g.contiguous(memory_format=torch.channels_last_3d), g):
+            d, f = depth.clone().requires_grad_(), feat.clone().requires_grad_()
+            bev = view(d, f, rots, trans, memory_format=torch.channels_last_3d)
+            assert bev.shape == ref.shape and bev.is_contiguous(memory_format=torch.channels_last_3d)
+            if det:
+                assert torch.equal(bev, ref)
+            else:
+                assert rel_to_max(bev.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= TOL
+            bev.backward(g_in)
+            assert torch.equal(d.grad, d0.grad) and torch.equal(f.grad, f0.grad)
+
+
+@pytest.mark.parametrize("name", ["tiny_bev_z1", "tiny_occ_z16", "tiny_omnihd", "tiny_hires"])
+def test_scatter_forward_ranks_bit_exact_vs_reference_golden(pkg, orc, name):
+    """Sort-free forward: the ranks it computes in-kernel (point_rank, the table the backward walks) must be the
+    reference's voxel ranks bit for bit, and its BEV grid must match the float64 oracle on the golden geometry."""
+    g = load(name)
+    B, N, D, H, W = g["coor"].shape[:5]
+    dx, bx, nx = (torch.from_numpy(g[k]) for k in ("dx", "bx", "nx"))
+    X, Y, Z = (int(v) for v in nx)
+    C = 8
+    vt = pkg.view_transform
+
+    class V:            # the attributes _view_forward_scatter reads
+        pass
+    v = V()
+    v.dx, v.bx, v.nx, v.frustum = dx, bx, nx, cu(g["frustum"])
+    rng = np.random.default_rng(1)
+    depth = rng.random((B, N, D, H, W), dtype=np.float32)
+    feat_cl = rng.standard_normal((B, N, H, W, C)).astype(np.float32)
+    # the stored cumsum_pooled of the tiny goldens is the REFERENCE's own CPU pooling of its own depth/feat
+    if "cumsum_pooled" in g.files and g["feat"].shape[2] == C:
+        depth, feat_cl = g["depth"], np.ascontiguousarray(g["feat"].transpose(0, 1, 3, 4, 2))
+    for layout, shape in ((pkg._lib.LAYOUT_BZYXC, (B, Z, Y, X, C)), (pkg._lib.LAYOUT_BCZYX, (B, C, Z, Y, X))):
+        out = torch.full(shape, 7.0, device=DEV)
+        pr = vt._view_forward_scatter(cu(depth), cu(feat_cl), out, v, cu(g["rots"]), cu(g["trans"]), B, N, D, H, W, C,
+                                      B, Z * Y, layout)
+        want_rank = orc.voxel_rank(g["coor"], g["dx"], g["bx"], g["nx"]).reshape(-1)
+        assert np.array_equal(pr.point_rank.cpu().numpy().astype(np.int64), want_rank)
+        rb, rd, rf, st, ln = orc.prepare_v2(g["coor"], g["dx"], g["bx"], g["nx"])
+        ref = orc.bev_pool_v2_forward(depth, feat_cl, rd, rf, rb, (B, Z, Y, X, C), st, ln, exact=True)
+        got = out if layout == pkg._lib.LAYOUT_BZYXC else out.permute(0, 2, 3, 4, 1)
+        assert rel_to_max(got.cpu().numpy(), ref) <= TOL
+        if "cumsum_pooled" in g.files and g["feat"].shape[2] == C:      # cumsum is the inexact party: 1e-4
+            assert rel_to_max(got.permute(0, 4, 1, 2, 3).cpu().numpy(), g["cumsum_pooled"]) <= 1e-4
