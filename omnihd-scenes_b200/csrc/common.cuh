@@ -233,11 +233,11 @@ __device__ __forceinline__ void cam_point(const float* __restrict__ frustum, con
 
 __device__ __forceinline__ bool voxel_index(float c, float lo, float dx, int n, int& v) {
   const float q = __fdiv_rn(__fsub_rn(c, lo), dx);
-  // .long(): truncation toward zero; NaN / beyond int64 come out as INT64_MIN on the CPU -> dropped
-  if (!(fabsf(q) < 9.0e18f)) return false;
-  const long long t = (long long)q;
-  v = (int)t;
-  return t >= 0 && t < n;
+  // .long() truncates toward zero, so (-1, 0) lands in voxel 0 and is KEPT; trunc(q) in [0, n) <=> -1 < q < n
+  // (n < 2^24 is exact in fp32). NaN / inf fail both comparisons (the CPU's INT64_MIN is dropped too).
+  if (!(q > -1.0f && q < (float)n)) return false;
+  v = (int)q;
+  return true;
 }
 
 }  // namespace bevpool

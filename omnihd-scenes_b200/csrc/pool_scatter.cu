@@ -51,8 +51,10 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
                         const float* __restrict__ rots, const float* __restrict__ trans, ScatterParams prm,
                         int* __restrict__ point_rank, float* __restrict__ acc_grid) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int4* s_rank4 = reinterpret_cast<int4*>(smem_raw);                               // [d][8]: ranks of rows h0..h0+3
-  float4* s_depth4 = reinterpret_cast<float4*>(s_rank4 + (size_t)prm.d * kScW);    // [d][8]
+  const int d_pad = (prm.d + 3) & ~3;
+  int4* s_rank4 = reinterpret_cast<int4*>(smem_raw);                               // [d_pad][8]: ranks of rows h0..h0+3
+  float4* s_depth4 = reinterpret_cast<float4*>(s_rank4 + (size_t)d_pad * kScW);    // [d_pad][8]
+  int* s_lead = reinterpret_cast<int*>(s_depth4 + (size_t)d_pad * kScW);           // [d_pad][8]: see below
   __shared__ float s_cam[12];
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const int c4 = CH4 ? CH4 : (prm.c >> 2);
@@ -74,6 +76,10 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
     __syncthreads();
   }
   // ---- stage ranks / depths of the block: 8 consecutive w = one 32-byte sector per (d, h)
+  if (threadIdx.x < (d_pad - prm.d) * kScW) {
+    s_lead[prm.d * kScW + threadIdx.x] = -1;
+    s_depth4[prm.d * kScW + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   {
     const int hl = lane >> 3, wl = lane & 7;
     const bool in = h0 + hl < prm.h && w0 + wl < prm.w;
@@ -107,9 +113,15 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int dd = d0 + k * kScWarps + warp;
+        // column summary for the walk: -1 nothing kept, rank >= 0 all kept rows share that voxel, -2 mixed
+        int lead = max(r[k], __shfl_xor_sync(kFullMask, r[k], 8));
+        lead = max(lead, __shfl_xor_sync(kFullMask, lead, 16));
+        const unsigned agree = __ballot_sync(kFullMask, r[k] < 0 || r[k] == lead);
+        const bool shared = ((agree >> wl) & 0x01010101u) == 0x01010101u;
         if (dd < prm.d) {
           reinterpret_cast<int*>(s_rank4 + dd * kScW + wl)[hl] = r[k];
           reinterpret_cast<float*>(s_depth4 + dd * kScW + wl)[hl] = r[k] >= 0 ? dv[k] : 0.f;   // dropped: weight 0
+          if (hl == 0) s_lead[dd * kScW + wl] = lead < 0 ? -1 : (shared ? lead : -2);
         }
       }
     }
@@ -131,6 +143,7 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
   float* grid_lane = acc_grid + lane_c;
   const int4* rank_col = s_rank4 + warp;
   const float4* depth_col = s_depth4 + warp;
+  const int* lead_col = s_lead + warp;
 
   // point (row p, rank rp, depth dp): join the accumulator holding voxel rp, else evict row p's accumulator
 #define BEVPOOL_SC_PUT(p, rp, dp)                                                        \
@@ -146,28 +159,29 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
     }                                                                                    \
   }
 
+  // The arrays are padded to a multiple of 4 bins (pad bins: lead = -1), so the loop needs no bounds tests and
+  // every shared-memory access has an immediate offset. lead is the same in all lanes; routing it through a warp
+  // reduction puts it in a UNIFORM register, so the branches below compile to uniform branches (no BSSY/BSYNC
+  // reconvergence bookkeeping, which was a third of this loop's instructions).
+  int cur0 = -1;
   for (int d0 = 0; d0 < prm.d; d0 += 4) {
-    int4 r[4];
+    int lead[4];
     float4 dp[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int dd = min(d0 + u, prm.d - 1);
-      r[u] = rank_col[dd * kScW];        // broadcast LDS.128
-      dp[u] = depth_col[dd * kScW];
-      if (d0 + u >= prm.d) r[u] = make_int4(-1, -1, -1, -1);
+      lead[u] = lead_col[(d0 + u) * kScW];     // broadcast LDS
+      dp[u] = depth_col[(d0 + u) * kScW];      // broadcast LDS.128
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int lead = max(max(r[u].x, r[u].y), max(r[u].z, r[u].w));
-      if (lead < 0) continue;   // warp-uniform: nothing kept in this bin
-      // fast path (every bin of a Z == 1 grid, most bins otherwise): all kept rows of the column share ONE voxel.
-      // One comparison against the open accumulator, then four unconditional FMAs (dropped rows weigh 0).
-      const bool shared = (r[u].x < 0 || r[u].x == lead) && (r[u].y < 0 || r[u].y == lead) &&
-                          (r[u].z < 0 || r[u].z == lead) && (r[u].w < 0 || r[u].w == lead);
-      if (shared) {
-        if (lead != cur[0]) {
-          if (cur[0] >= 0 && act) red_add_f32x4(grid_lane + (int64_t)cur[0] * C, acc[0]);
-          cur[0] = lead;
+      const int lu = __reduce_max_sync(kFullMask, lead[u]);
+      if (lu == -1) continue;   // nothing kept in this bin
+      if (lu >= 0) {
+        // fast path (every bin of a Z == 1 grid, most bins otherwise): all kept rows of the column share ONE
+        // voxel. One comparison against the open accumulator, four unconditional FMAs (dropped rows weigh 0).
+        if (lu != cur0) {
+          if (cur0 >= 0 && act) red_add_f32x4(grid_lane + (int64_t)cur0 * C, acc[0]);
+          cur0 = lu;
           acc[0] = zero;
         }
         acc[0] = fma4(fv[0], dp[u].x, acc[0]);
@@ -176,12 +190,16 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
         acc[0] = fma4(fv[3], dp[u].w, acc[0]);
         continue;
       }
-      BEVPOOL_SC_PUT(0, r[u].x, dp[u].x)
-      BEVPOOL_SC_PUT(1, r[u].y, dp[u].y)
-      BEVPOOL_SC_PUT(2, r[u].z, dp[u].z)
-      BEVPOOL_SC_PUT(3, r[u].w, dp[u].w)
+      cur[0] = cur0;
+      const int4 r = rank_col[(d0 + u) * kScW];
+      BEVPOOL_SC_PUT(0, r.x, dp[u].x)
+      BEVPOOL_SC_PUT(1, r.y, dp[u].y)
+      BEVPOOL_SC_PUT(2, r.z, dp[u].z)
+      BEVPOOL_SC_PUT(3, r.w, dp[u].w)
+      cur0 = __reduce_max_sync(kFullMask, cur[0]);
     }
   }
+  cur[0] = cur0;
 #undef BEVPOOL_SC_PUT
   if (act) {
 #pragma unroll
@@ -258,7 +276,7 @@ static int view_forward_t(const void* depth, const void* feat, const float* frus
   prm.blocks_h = (prm.h + kScH - 1) / kScH;
   const int64_t blocks = (int64_t)prm.bn * prm.blocks_w * prm.blocks_h;
   if (blocks > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
-  const size_t smem = (size_t)prm.d * kScW * (sizeof(int4) + sizeof(float4));
+  const size_t smem = (size_t)((prm.d + 3) & ~3) * kScW * (sizeof(int4) + sizeof(float4) + sizeof(int));
   if (smem > 200 * 1024) return BEVPOOL_ERR_BAD_ARG;
   if (blocks > 0) {
     switch (prm.c) {
