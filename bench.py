@@ -167,7 +167,7 @@ def run_native_arm(args):
     B = cfg.batch if args.frames is None else args.frames     # frames per GPU (weak scaling)
     dt_t = torch.bfloat16 if cfg.dtype == "bf16" else torch.float32
     groups = args.frame_groups if B % max(args.frame_groups, 1) == 0 else 1
-    view = pkg.LSSViewTransform.from_config(cfg, frame_groups=groups).to(dev)
+    view = pkg.LSSViewTransform.from_config(cfg, frame_groups=groups, deterministic=args.deterministic).to(dev)
     X, Y, Z = (int(v) for v in view.nx)
     C, D, H, W, N = cfg.channels, view.D, view.fH, view.fW, cfg.n_cams
     V, F, P0 = B * X * Y * Z, B * N * H * W, B * N * D * H * W
@@ -377,6 +377,11 @@ def run_native_arm(args):
                                           sets[k]["depth"].data_ptr(), feat_cl[k].data_ptr(), p.point_rank.data_ptr(),
                                           p.bn, p.d, p.h, p.w, C, 1, 1 if Z == 1 else 0, code, st)
 
+        def k_view(i):      # default forward: memset + view_fwd_scatter (geometry, ranks, pooling) + layout pass
+            k = i % N_BUFFER_SETS
+            pkg.view_transform._view_forward_scatter(sets[k]["depth"].detach(), feat_cl[k], outs[k], view, sets[k]["rots"],
+                                                     sets[k]["trans"], B, N, D, H, W, C, B, Z * Y, pkg._lib.LAYOUT_BCZYX)
+
         def k_prep(i):
             k = i % N_BUFFER_SETS
             pkg.view_transform._prepare_device(None, view.frustum, sets[k]["rots"], sets[k]["trans"], B, N, D, H, W,
@@ -384,7 +389,8 @@ def run_native_arm(args):
 
         reps = 40
         for name, fn in (("pool_fwd_dense", k_fwd), ("grid_transpose", k_tr), ("pool_bwd_dense", k_bwd),
-                         ("prepare_all", k_prep), ("feat_transpose", k_trf), ("voxel_table", k_tbl)):
+                         ("prepare_all", k_prep), ("feat_transpose", k_trf), ("voxel_table", k_tbl),
+                         ("view_forward", k_view)):
             kernels[name] = timed_local(torch, fn, reps) * 1e-3      # seconds per launch
 
     if rank != 0:
@@ -399,8 +405,10 @@ def run_native_arm(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
-    # pool_fwd_dense = chunk kernel + fix-up + layout pass (3 launches); pool_bwd_dense is ONE kernel and the
-    # largest single launch of the step, so it is the kernel the roofline is reported for.
+    # The step's default path is: feat transpose, view_forward (memset + view_fwd_scatter + acc_layout), out_grad
+    # transpose, pool_bwd_dense. pool_bwd_dense is ONE kernel and the largest single launch of the step, so it is
+    # the kernel the roofline is reported for. prepare / voxel_table / pool_fwd_dense are the deterministic
+    # (sorted) alternative of view_forward and are timed for comparison.
     dom = "pool_bwd_dense"
     dom_bytes = ab["bwd"]
     achieved = dom_bytes / kernels[dom] / 1e9
@@ -415,7 +423,10 @@ def run_native_arm(args):
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "us_per_launch": kernels[dom] * 1e6,
                 "all_kernels": {
-                    "pool_fwd_dense(chunk+fixup+layout, 3 launches)": {
+                    "view_forward(memset+scatter+layout; geometry, ranks and pooling, default path)": {
+                        "us": kernels["view_forward"] * 1e6, "GBps": ab["fwd"] / kernels["view_forward"] / 1e9,
+                        "bytes": ab["fwd"]},
+                    "pool_fwd_dense(chunk+fixup+layout, 3 launches; deterministic path)": {
                         "us": kernels["pool_fwd_dense"] * 1e6, "GBps": ab["fwd"] / kernels["pool_fwd_dense"] / 1e9,
                         "bytes": ab["fwd"]},
                     "pool_bwd_dense": {"us": kernels["pool_bwd_dense"] * 1e6, "GBps": ab["bwd"] / kernels["pool_bwd_dense"] / 1e9,
@@ -424,8 +435,8 @@ def run_native_arm(args):
                                                  "GBps": 2 * e * C * V / kernels["grid_transpose"] / 1e9},
                     "feat_transpose": {"us": kernels["feat_transpose"] * 1e6,
                                        "GBps": 2 * e * C * F / kernels["feat_transpose"] / 1e9},
-                    "voxel_table": {"us": kernels["voxel_table"] * 1e6},
-                    "prepare(all kernels, eager launches)": {"us": kernels["prepare_all"] * 1e6, "bytes_out": ab["prep"]}},
+                    "voxel_table(deterministic path)": {"us": kernels["voxel_table"] * 1e6},
+                    "prepare(all kernels, eager launches; deterministic path)": {"us": kernels["prepare_all"] * 1e6, "bytes_out": ab["prep"]}},
                 "step_GBps_fwd_plus_bwd": (ab["fwd"] + ab["bwd"]) / (ms_step * 1e-3) / 1e9}
 
     # ---- (4) CPU baseline (N=1 only): the reference's PyTorch cumsum path on this box's host cores
@@ -448,7 +459,8 @@ def run_native_arm(args):
         "vs_baseline": None, "dtype": "bf16" if dt_t == torch.bfloat16 else "f32", "data": "synthetic",
         "config": {"workload": args.config, "frames_per_gpu": B, "cams": N, "feat": [H, W], "D": D, "C": C,
                    "grid": [X, Y, Z], "P0": P0, "P": P, "I": I,
-                   "step": "geometry+prepare+fwd+bwd (public API, one CUDA graph per buffer set)",
+                   "step": "geometry+ranks+fwd+bwd (LSSViewTransform.forward + backward, one CUDA graph per buffer set)",
+                   "forward_path": "deterministic(sorted)" if view.deterministic else "scatter(sort-free, fp32 REDs)",
                    "frame_groups": groups,
                    "l2": f"inputs rotated over {N_BUFFER_SETS} buffer sets (> 126 MB L2 in total), no explicit flush",
                    "parallelism": f"frame-sharded x{world}, no collective on the path"},
@@ -485,7 +497,9 @@ def main():
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU (default: the config's batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the channels_last_3d variant measurement")
-    ap.add_argument("--frame-groups", type=int, default=4,
+    ap.add_argument("--deterministic", action="store_true",
+                    help="fused forward through the sorted, fixed-summation-order path instead of the sort-free scatter")
+    ap.add_argument("--frame-groups", type=int, default=2,
                     help="independent frame groups run on concurrent streams inside one step (1 = single stream)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -756,10 +756,12 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
                       T* __restrict__ feat_grad) {
   constexpr int C = CH4 * 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int4* s_rank4 = reinterpret_cast<int4*>(smem_raw);                               // [d][8]: ranks of rows h0..h0+3
-  float4* s_depth4 = reinterpret_cast<float4*>(s_rank4 + (size_t)prm.d * kPixW);   // [d][8]: 0 where dropped
-  float4* s_dg4 = s_depth4 + (size_t)prm.d * kPixW;                                // [d][8]
-  float* s_part = reinterpret_cast<float*>(s_dg4 + (size_t)prm.d * kPixW);         // [8 warps][8 bins][C]; later [C][33]
+  const int d_pad = (prm.d + kJointBins - 1) / kJointBins * kJointBins;             // pad bins: lead = -1
+  int4* s_rank4 = reinterpret_cast<int4*>(smem_raw);                               // [d_pad][8]: ranks of rows h0..h0+3
+  float4* s_depth4 = reinterpret_cast<float4*>(s_rank4 + (size_t)d_pad * kPixW);   // [d_pad][8]: 0 where dropped
+  float4* s_dg4 = s_depth4 + (size_t)d_pad * kPixW;                                // [d_pad][8]
+  int* s_lead = reinterpret_cast<int*>(s_dg4 + (size_t)d_pad * kPixW);             // [d_pad][8] column summaries
+  float* s_part = reinterpret_cast<float*>(s_lead + (size_t)d_pad * kPixW);        // [8 warps][8 bins][C]; later [C][33]
   float* s_fg = s_part;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -778,6 +780,7 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
 
   // ---- stage point_rank / depth of the block: 8 consecutive w = one 32-byte sector per (d, h);
   //      8 bins per thread are loaded before anything is stored (one memory latency, not eight)
+  if (threadIdx.x < (d_pad - prm.d) * kPixW) s_lead[prm.d * kPixW + threadIdx.x] = -1;
   {
     const int hl = lane >> 3, wl = lane & 7;
     const bool in = h0 + hl < prm.h && w0 + wl < prm.w;
@@ -798,9 +801,16 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int dd = d0 + k * kBwdWarps + warp;
+        // column summary: -1 nothing kept; rank >= 0: every kept row of the column sits in that voxel;
+        // -2 - rank: mixed column whose largest rank is `rank`
+        int lead = max(r[k], __shfl_xor_sync(kFullMask, r[k], 8));
+        lead = max(lead, __shfl_xor_sync(kFullMask, lead, 16));
+        const unsigned agree = __ballot_sync(kFullMask, r[k] < 0 || r[k] == lead);
+        const bool shared = ((agree >> wl) & 0x01010101u) == 0x01010101u;
         if (dd < prm.d) {
           reinterpret_cast<int*>(s_rank4 + dd * kPixW + wl)[hl] = r[k];
           reinterpret_cast<float*>(s_depth4 + dd * kPixW + wl)[hl] = r[k] >= 0 ? dv[k] : 0.f;
+          if (hl == 0) s_lead[dd * kPixW + wl] = lead < 0 ? -1 : (shared ? lead : -2 - lead);
         }
       }
     }
@@ -824,46 +834,41 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
   if (ww < prm.w) {   // warp-uniform
     const int4* rank_col = s_rank4 + warp;
     const float4* depth_col = s_depth4 + warp;
+    const int* lead_col = s_lead + warp;
     for (int d0 = 0; d0 < prm.d; d0 += kJointBins) {
 #pragma unroll
       for (int k0 = 0; k0 < kJointBins; k0 += 4) {
-        // 4 bins at a time: lead rows requested first, then consumed
-        int4 r[4];
-        int lead[4];
+        // 4 bins at a time: lead rows requested first, then consumed (the summaries are identical in all lanes)
+        int code[4];
         float4 g[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int dd = d0 + k0 + u;
-          r[u] = dd < prm.d ? rank_col[dd * kPixW] : make_int4(-1, -1, -1, -1);   // broadcast
-          lead[u] = max(max(r[u].x, r[u].y), max(r[u].z, r[u].w));                 // any kept rank (-1: none)
+          code[u] = lead_col[(d0 + k0 + u) * kPixW];   // broadcast LDS
           g[u] = zero;
-          if (lead[u] >= 0) g[u] = Vec4<T>::load(og_lane, (int64_t)lead[u] * C);
+          if (code[u] != -1) g[u] = Vec4<T>::load(og_lane, (int64_t)(code[u] >= 0 ? code[u] : -2 - code[u]) * C);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (lead[u] < 0) continue;   // warp-uniform
+          if (code[u] == -1) continue;
           const int dd = d0 + k0 + u;
           const float4 dp = depth_col[dd * kPixW];
-          const int rr[kPixH] = {r[u].x, r[u].y, r[u].z, r[u].w};
           const float dw[kPixH] = {dp.x, dp.y, dp.z, dp.w};
           float dt[kPixH];
-          const bool shared = (rr[0] < 0 || rr[0] == lead[u]) && (rr[1] < 0 || rr[1] == lead[u]) &&
-                              (rr[2] < 0 || rr[2] == lead[u]) && (rr[3] < 0 || rr[3] == lead[u]);
-          if (shared) {   // every kept pixel of the column sits in the lead voxel
+          if (code[u] >= 0) {   // every kept pixel of the column sits in the lead voxel; dropped rows weigh 0
 #pragma unroll
             for (int p = 0; p < kPixH; ++p) {
-              dt[p] = 0.f;
-              if (rr[p] >= 0) {   // warp-uniform predicate
-                fg[p] = fma4(g[u], dw[p], fg[p]);
-                dt[p] = dot4_packed(g[u], fv[p]);
-              }
+              fg[p] = fma4(g[u], dw[p], fg[p]);
+              dt[p] = dot4_packed(g[u], fv[p]);   // dropped rows: discarded by the reducing lane below
             }
           } else {
+            const int lead = -2 - code[u];
+            const int4 r4 = rank_col[dd * kPixW];
+            const int rr[kPixH] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
             for (int p = 0; p < kPixH; ++p) {
               dt[p] = 0.f;
               if (rr[p] >= 0) {
-                const float4 gp = rr[p] == lead[u] ? g[u] : Vec4<T>::load(og_lane, (int64_t)rr[p] * C);
+                const float4 gp = rr[p] == lead ? g[u] : Vec4<T>::load(og_lane, (int64_t)rr[p] * C);
                 fg[p] = fma4(gp, dw[p], fg[p]);
                 dt[p] = dot4_packed(gp, fv[p]);
               }
@@ -1042,7 +1047,8 @@ static int backward_joint_launch(const void* og, void* dg, void* fg, const void*
   size_t part_bytes = sizeof(float) * (size_t)kBwdWarps * kJointBins * (C + 4);
   const size_t fg_bytes = prm.feat_grad_nchw ? sizeof(float) * (size_t)C * kJointPad : 0;
   if (fg_bytes > part_bytes) part_bytes = fg_bytes;
-  const size_t smem = (size_t)3 * prm.d * kPixW * 16 + part_bytes;
+  const size_t d_pad = (size_t)(prm.d + kJointBins - 1) / kJointBins * kJointBins;
+  const size_t smem = d_pad * kPixW * (3 * 16 + 4) + part_bytes;
   if (smem > 200 * 1024) return BEVPOOL_ERR_BAD_ARG;
   auto kern = pool_bwd_joint_kernel<T, CH4>;
   static size_t attr = 0;

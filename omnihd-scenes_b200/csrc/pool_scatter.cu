@@ -160,9 +160,8 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
   }
 
   // The arrays are padded to a multiple of 4 bins (pad bins: lead = -1), so the loop needs no bounds tests and
-  // every shared-memory access has an immediate offset. lead is the same in all lanes; routing it through a warp
-  // reduction puts it in a UNIFORM register, so the branches below compile to uniform branches (no BSSY/BSYNC
-  // reconvergence bookkeeping, which was a third of this loop's instructions).
+  // every shared-memory access has an immediate offset. (Routing the summaries through a warp reduction to get
+  // them into uniform registers removes the BSSY/BSYNC bookkeeping but CREDUX costs as much: measured equal.)
   int cur0 = -1;
   for (int d0 = 0; d0 < prm.d; d0 += 4) {
     int lead[4];
@@ -174,7 +173,7 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int lu = __reduce_max_sync(kFullMask, lead[u]);
+      const int lu = lead[u];
       if (lu == -1) continue;   // nothing kept in this bin
       if (lu >= 0) {
         // fast path (every bin of a Z == 1 grid, most bins otherwise): all kept rows of the column share ONE
@@ -196,7 +195,7 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
       BEVPOOL_SC_PUT(1, r.y, dp[u].y)
       BEVPOOL_SC_PUT(2, r.z, dp[u].z)
       BEVPOOL_SC_PUT(3, r.w, dp[u].w)
-      cur0 = __reduce_max_sync(kFullMask, cur[0]);
+      cur0 = cur[0];
     }
   }
   cur[0] = cur0;
