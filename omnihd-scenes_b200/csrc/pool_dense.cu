@@ -780,7 +780,10 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
 
   // ---- stage point_rank / depth of the block: 8 consecutive w = one 32-byte sector per (d, h);
   //      8 bins per thread are loaded before anything is stored (one memory latency, not eight)
-  if (threadIdx.x < (d_pad - prm.d) * kPixW) s_lead[prm.d * kPixW + threadIdx.x] = -1;
+  if (threadIdx.x < (d_pad - prm.d) * kPixW) {   // pad bins: empty, weight 0 (they ride through the straight-line path)
+    s_lead[prm.d * kPixW + threadIdx.x] = -1;
+    s_depth4[prm.d * kPixW + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   {
     const int hl = lane >> 3, wl = lane & 7;
     const bool in = h0 + hl < prm.h && w0 + wl < prm.w;
@@ -846,6 +849,26 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
           code[u] = lead_col[(d0 + k0 + u) * kPixW];   // broadcast LDS
           g[u] = zero;
           if (code[u] != -1) g[u] = Vec4<T>::load(og_lane, (int64_t)(code[u] >= 0 ? code[u] : -2 - code[u]) * C);
+        }
+        const int cmax = max(max(code[0], code[1]), max(code[2], code[3]));
+        const int cmin = min(min(code[0], code[1]), min(code[2], code[3]));
+        if (cmax == -1) continue;   // warp-uniform: the 4 bins are empty (dropped points come in long runs)
+        if (cmin >= -1) {
+          // no mixed column among the 4 bins: straight-line code, no per-bin branches. Empty bins ride along with
+          // g = 0 and weights 0 (their partials are discarded by the reducing lane below).
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 dp = depth_col[(d0 + k0 + u) * kPixW];
+            const float dw[kPixH] = {dp.x, dp.y, dp.z, dp.w};
+            float dt[kPixH];
+#pragma unroll
+            for (int p = 0; p < kPixH; ++p) {
+              fg[p] = fma4(g[u], dw[p], fg[p]);
+              dt[p] = dot4_packed(g[u], fv[p]);
+            }
+            if (act) *reinterpret_cast<float4*>(my_part + (k0 + u) * PS) = make_float4(dt[0], dt[1], dt[2], dt[3]);
+          }
+          continue;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
