@@ -388,9 +388,10 @@ def run_native_arm(args):
                                                view.dx, view.bx, view.nx, dev, want_intervals=False)
 
         reps = 40
-        for name, fn in (("pool_fwd_dense", k_fwd), ("grid_transpose", k_tr), ("pool_bwd_dense", k_bwd),
-                         ("prepare_all", k_prep), ("feat_transpose", k_trf), ("voxel_table", k_tbl),
-                         ("view_forward", k_view)):
+        todo = [("grid_transpose", k_tr), ("pool_bwd_dense", k_bwd), ("feat_transpose", k_trf), ("view_forward", k_view)]
+        if args.deterministic or args.time_sorted_path:      # the sorted alternative of view_forward
+            todo += [("pool_fwd_dense", k_fwd), ("prepare_all", k_prep), ("voxel_table", k_tbl)]
+        for name, fn in todo:
             kernels[name] = timed_local(torch, fn, reps) * 1e-3      # seconds per launch
 
     if rank != 0:
@@ -428,15 +429,16 @@ def run_native_arm(args):
                         "bytes": ab["fwd"]},
                     "pool_fwd_dense(chunk+fixup+layout, 3 launches; deterministic path)": {
                         "us": kernels["pool_fwd_dense"] * 1e6, "GBps": ab["fwd"] / kernels["pool_fwd_dense"] / 1e9,
-                        "bytes": ab["fwd"]},
+                        "bytes": ab["fwd"]} if "pool_fwd_dense" in kernels else None,
                     "pool_bwd_dense": {"us": kernels["pool_bwd_dense"] * 1e6, "GBps": ab["bwd"] / kernels["pool_bwd_dense"] / 1e9,
                                        "bytes": ab["bwd"]},
                     "grid_transpose(out_grad)": {"us": kernels["grid_transpose"] * 1e6,
                                                  "GBps": 2 * e * C * V / kernels["grid_transpose"] / 1e9},
                     "feat_transpose": {"us": kernels["feat_transpose"] * 1e6,
                                        "GBps": 2 * e * C * F / kernels["feat_transpose"] / 1e9},
-                    "voxel_table(deterministic path)": {"us": kernels["voxel_table"] * 1e6},
-                    "prepare(all kernels, eager launches; deterministic path)": {"us": kernels["prepare_all"] * 1e6, "bytes_out": ab["prep"]}},
+                    "voxel_table(deterministic path)": {"us": kernels["voxel_table"] * 1e6} if "voxel_table" in kernels else None,
+                    "prepare(all kernels, eager launches; deterministic path)":
+                        {"us": kernels["prepare_all"] * 1e6, "bytes_out": ab["prep"]} if "prepare_all" in kernels else None},
                 "step_GBps_fwd_plus_bwd": (ab["fwd"] + ab["bwd"]) / (ms_step * 1e-3) / 1e9}
 
     # ---- (4) CPU baseline (N=1 only): the reference's PyTorch cumsum path on this box's host cores
@@ -445,7 +447,7 @@ def run_native_arm(args):
         step, threads = cpu_reference_step_factory(args.config, 1)
         step()
         reps, t0 = 0, time.perf_counter()
-        while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 50):
+        while reps < 3 or (time.perf_counter() - t0 < 12.0 and reps < 400):
             step()
             reps += 1
         dt = time.perf_counter() - t0
@@ -497,6 +499,8 @@ def main():
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU (default: the config's batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the channels_last_3d variant measurement")
+    ap.add_argument("--time-sorted-path", action="store_true",
+                    help="also time the kernels of the sorted (deterministic) forward for comparison")
     ap.add_argument("--deterministic", action="store_true",
                     help="fused forward through the sorted, fixed-summation-order path instead of the sort-free scatter")
     ap.add_argument("--frame-groups", type=int, default=2,
