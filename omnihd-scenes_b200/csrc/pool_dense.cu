@@ -884,14 +884,21 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
               dt[p] = dot4_packed(g[u], fv[p]);   // dropped rows: discarded by the reducing lane below
             }
           } else {
+            // mixed column: rows of one voxel are adjacent (height is monotonic along the column), so a row is
+            // loaded once per RUN of equal ranks; the largest rank's row is already in g[u]
             const int lead = -2 - code[u];
             const int4 r4 = rank_col[dd * kPixW];
             const int rr[kPixH] = {r4.x, r4.y, r4.z, r4.w};
+            float4 gp = g[u];
+            int rp = lead;
 #pragma unroll
             for (int p = 0; p < kPixH; ++p) {
               dt[p] = 0.f;
               if (rr[p] >= 0) {
-                const float4 gp = rr[p] == lead ? g[u] : Vec4<T>::load(og_lane, (int64_t)rr[p] * C);
+                if (rr[p] != rp) {
+                  rp = rr[p];
+                  gp = rp == lead ? g[u] : Vec4<T>::load(og_lane, (int64_t)rp * C);
+                }
                 fg[p] = fma4(gp, dw[p], fg[p]);
                 dt[p] = dot4_packed(gp, fv[p]);
               }
