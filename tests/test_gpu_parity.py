@@ -309,7 +309,8 @@ def test_backward_general_path_vs_oracle(pkg, orc, case):
         assert rel_to_max(f.grad.cpu().numpy(), gf) <= TOL
 
 
-@pytest.mark.parametrize("cfg_name,B", [("bevdet_r50_b8", 8), ("occ_200x200x16_b64", 2), ("bevdepth_hires_b16", 1)])
+@pytest.mark.parametrize("cfg_name,B", [("bevdet_r50_b8", 8), ("occ_200x200x16_b64", 2), ("bevdepth_hires_b16", 1),
+                                        ("rcfusion_omnihd_b32", 1)])
 def test_view_transform_fwd_bwd_vs_oracle(pkg, orc, cfg_name, B):
     """Public API end to end at BASELINE sizes: get_geometry -> voxel_pooling_v2 (prepare + bev_pool_v2 with
     the sort-free backward) and the fully fused module forward; both against the float64 oracle."""
@@ -606,3 +607,27 @@ def test_scatter_forward_ranks_bit_exact_vs_reference_golden(pkg, orc, name):
         assert rel_to_max(got.cpu().numpy(), ref) <= TOL
         if "cumsum_pooled" in g.files and g["feat"].shape[2] == C:      # cumsum is the inexact party: 1e-4
             assert rel_to_max(got.permute(0, 4, 1, 2, 3).cpu().numpy(), g["cumsum_pooled"]) <= 1e-4
+
+
+def test_deterministic_switch(pkg):
+    """deterministic=True (or torch.use_deterministic_algorithms) runs the sorted forward: bit-identical from run to
+    run; the default sort-free forward agrees with it to fp32 summation noise; the backward is the same kernel."""
+    cfg = pkg.synthetic.CONFIGS["bevdet_r50_b8"]
+    B, N, C = 4, cfg.n_cams, cfg.channels
+    view = pkg.LSSViewTransform.from_config(cfg, deterministic=True).to(DEV)
+    rots, trans = pkg.synthetic.camera_ring(B, N, cfg.final_dim, seed=9)
+    rots, trans = rots.to(DEV), trans.to(DEV)
+    torch.manual_seed(9)
+    depth = torch.randn(B, N, view.D, view.fH, view.fW, device=DEV).softmax(2)
+    feat = torch.randn(B, N, C, view.fH, view.fW, device=DEV)
+    a, b = view(depth, feat, rots, trans), view(depth, feat, rots, trans)
+    assert torch.equal(a, b)
+    view.deterministic = False
+    c = view(depth, feat, rots, trans)
+    assert rel_to_max(c.cpu().numpy(), a.cpu().numpy()) <= TOL
+    torch.use_deterministic_algorithms(True)
+    try:
+        d = view(depth, feat, rots, trans)
+    finally:
+        torch.use_deterministic_algorithms(False)
+    assert torch.equal(d, a)
