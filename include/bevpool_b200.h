@@ -208,6 +208,19 @@ int bevpool_lift_forward(const void* x, void* depth, void* feat, int bn, int d, 
 int bevpool_lift_backward(const void* depth, const void* depth_grad, const void* feat_grad, void* x_grad,
                           int bn, int d, int c, int hw, int feat_channels_last, int dtype, void* stream);
 
+/* ------------------------------------------------------------------ pillar scatter
+ * `pts_middle_encoder` of the RCFusion detector (rcfusion/detectors/rcfusion_faster_rcnn.py:100; config
+ * RCFusion_NewScenes/rcfusion_lss.py:63-64) = mmdet3d v0.17.1 PointPillarsScatter (dependency, not in the tree):
+ * canvas [B, C, ny, nx] = zeros, canvas[b, :, y, x] = voxel_features[i, :] for coors[i] = (b, z, y, x) int32
+ * (16-byte aligned [P, 4]); the last pillar wins on duplicated cells. pillar_index: int32 [B, ny*nx] output
+ * (winning pillar per cell, -1 = empty). Every canvas element is written (no memset needed).
+ * Backward: voxel_grad [P, C] = canvas_grad[b, :, y, x]. */
+int bevpool_pillar_scatter_forward(const void* voxel_features, const int32_t* coors, void* canvas,
+                                   int32_t* pillar_index, int n_pillars, int c, int b, int ny, int nx, int dtype,
+                                   void* stream);
+int bevpool_pillar_scatter_backward(const void* canvas_grad, const int32_t* coors, void* voxel_grad, int n_pillars,
+                                    int c, int b, int ny, int nx, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

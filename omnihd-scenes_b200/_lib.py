@@ -48,6 +48,8 @@ SIGNATURES = {
     "bevpool_view_forward_scratch_bytes": (ctypes.c_size_t, [c_i64, c_int, c_int, c_int]),
     "bevpool_view_forward": (c_int, [c_void_p] * 5 + [ctypes.POINTER(GridT), c_int, c_void_p, c_int, c_void_p, c_i64, c_i64,
                                      c_int, c_int, c_void_p, ctypes.c_size_t, c_void_p]),
+    "bevpool_pillar_scatter_forward": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
+    "bevpool_pillar_scatter_backward": (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
     "bevpool_lift_forward": (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
     "bevpool_lift_backward": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     "bevpool_grid_transpose": (c_int, [c_void_p, c_void_p, c_int, c_int, c_i64, c_int, c_int, c_void_p]),

@@ -207,6 +207,27 @@ def lift_head_backward(depth, depth_grad, feat_grad):
     return np.concatenate([dx.astype(np.float32), np.asarray(feat_grad, dtype=np.float32)], axis=1)
 
 
+# --------------------------------------------------------------------------- pillar scatter
+def pillar_scatter(voxel_features, coors, batch_size, ny, nx):
+    """mmdet3d v0.17.1 PointPillarsScatter.forward_batch (the reference's pts_middle_encoder,
+    rcfusion_faster_rcnn.py:100; mmdet3d is a dependency outside the reference tree — PARITY UNPINNED for this
+    function: restated from the published algorithm, checked against torch index assignment in the tests):
+    per sample a zero canvas [C, ny*nx], canvas[:, y*nx + x] = features.T in pillar order (last wins)."""
+    f = np.asarray(voxel_features, dtype=np.float32)
+    co = np.asarray(coors).astype(np.int64)
+    out = np.zeros((batch_size, f.shape[1], ny * nx), dtype=np.float32)
+    for i in range(f.shape[0]):
+        b, _, y, x = co[i]
+        out[b, :, y * nx + x] = f[i]
+    return out.reshape(batch_size, f.shape[1], ny, nx)
+
+
+def pillar_scatter_backward(canvas_grad, coors):
+    g = np.asarray(canvas_grad, dtype=np.float32)
+    co = np.asarray(coors).astype(np.int64)
+    return np.stack([g[b, :, y, x] for b, _, y, x in co]) if len(co) else np.zeros((0, g.shape[1]), np.float32)
+
+
 # --------------------------------------------------------------------------- v1 op
 def bev_pool_v1(feats, coords, B, D, H, W):
     """ops/bev_pool/bev_pool.py:83-97 + src/bev_pool_cuda.cu:20-42: -> (out [B,C,D,H,W], order, starts, lengths)."""

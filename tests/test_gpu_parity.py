@@ -631,3 +631,36 @@ def test_deterministic_switch(pkg):
     finally:
         torch.use_deterministic_algorithms(False)
     assert torch.equal(d, a)
+
+
+# ------------------------------------------------------------------------------------------ pillar scatter (§8(f) rank 4)
+@pytest.mark.parametrize("B,C,ny,nx,P,dt", [(2, 64, 320, 480, 40000, torch.float32), (1, 64, 320, 480, 0, torch.float32),
+                                            (3, 7, 5, 13, 150, torch.float32), (2, 64, 33, 65, 3000, torch.bfloat16)])
+def test_pillar_scatter_vs_oracle(pkg, orc, B, C, ny, nx, P, dt):
+    """PointPillarsScatter drop-in at the RCFusion config size (64 channels, 320x480, 40 000 pillars), empty input,
+    duplicated cells (last pillar wins), out-of-range pillars (ignored), bf16 io; backward vs the oracle."""
+    rng = np.random.default_rng(B * 100 + C)
+    cells = rng.integers(0, B * ny * nx, size=P) if P and P > B * ny * nx // 2 else rng.permutation(B * ny * nx)[:P]
+    coors = np.stack([cells // (ny * nx), rng.integers(0, 3, size=P), (cells % (ny * nx)) // nx, cells % nx], 1).astype(np.int32)
+    feats = rng.standard_normal((P, C)).astype(np.float32)
+    ft = cu(feats).to(dt).requires_grad_()
+    fin = ft.detach().float().cpu().numpy()
+    m = pkg.pillar_scatter.PointPillarsScatter(C, [ny, nx])
+    out = m(ft, cu(coors), B)
+    assert out.shape == (B, C, ny, nx) and out.dtype == dt
+    assert np.array_equal(out.detach().float().cpu().numpy(), orc.pillar_scatter(fin, coors, B, ny, nx))
+    g = rng.standard_normal((B, C, ny, nx)).astype(np.float32)
+    gt = cu(g).to(dt)
+    out.backward(gt)
+    assert np.array_equal(ft.grad.float().cpu().numpy(), orc.pillar_scatter_backward(gt.float().cpu().numpy(), coors))
+    if P:   # pillars outside the canvas are dropped, their gradient is zero
+        bad = coors.copy()
+        bad[0] = (B, 0, 0, 0)
+        bad[-1] = (0, 0, ny, 0)
+        f2 = cu(feats).to(dt).requires_grad_()
+        out2 = m(f2, cu(bad), B)
+        keep = np.ones(P, bool)
+        keep[[0, P - 1]] = False
+        assert np.array_equal(out2.detach().float().cpu().numpy(), orc.pillar_scatter(fin[keep], bad[keep], B, ny, nx))
+        out2.backward(gt)
+        assert float(f2.grad[0].abs().max()) == 0.0 and float(f2.grad[-1].abs().max()) == 0.0

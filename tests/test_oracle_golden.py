@@ -166,3 +166,23 @@ def test_lift_head_matches_reference_camencode(orc):
     assert np.allclose(depth.sum(axis=1), 1.0, atol=1e-6)
     xg = orc.lift_head_backward(depth, g["depth_grad"], g["feat_grad"])
     assert rel_to_max(xg, g["x_grad"]) <= 1e-6
+
+
+def test_pillar_scatter_oracle_vs_torch_index_assignment(orc):
+    """§8(f) rank 4. mmdet3d (v0.17.1) is not in the reference tree, so this oracle is PARITY-UNPINNED against the
+    reference itself; it is checked against the torch CPU index assignment the published module performs."""
+    import torch
+    rng = np.random.default_rng(3)
+    B, C, ny, nx, P = 2, 5, 7, 9, 40
+    cells = rng.permutation(B * ny * nx)[:P]                      # unique pillars, as the voxeliser produces
+    coors = np.stack([cells // (ny * nx), np.zeros(P, np.int64), (cells % (ny * nx)) // nx, cells % nx], 1)
+    feats = rng.standard_normal((P, C)).astype(np.float32)
+    got = orc.pillar_scatter(feats, coors, B, ny, nx)
+    want = torch.zeros(B, C, ny * nx)
+    for b in range(B):
+        m = torch.from_numpy(coors[:, 0] == b)
+        idx = torch.from_numpy(coors[:, 2] * nx + coors[:, 3])[m]
+        want[b][:, idx] = torch.from_numpy(feats)[m].t()
+    assert np.array_equal(got, want.view(B, C, ny, nx).numpy())
+    g = rng.standard_normal(got.shape).astype(np.float32)
+    assert np.array_equal(orc.pillar_scatter_backward(g, coors), g[coors[:, 0], :, coors[:, 2], coors[:, 3]])
