@@ -732,6 +732,144 @@ pool_bwd_block_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
   }
 }
 
+// Same contract for C <= 64: a row is at most 16 lanes wide, so each HALF-warp takes its own pixel (own compacted
+// list, own out_grad rows, own 16-lane reduce-scatter) and a warp finishes two pixels per pass — twice the lane
+// utilisation of the kernel above on the OmniHD (C = 64) and occupancy (C = 32) shapes.
+template <typename T>
+__global__ void __launch_bounds__(kBwdThreads)
+pool_bwd_block_half_kernel(const T* __restrict__ og, const T* __restrict__ depth, const T* __restrict__ feat,
+                           const int* __restrict__ point_rank, BwdParams prm, T* __restrict__ depth_grad,
+                           T* __restrict__ feat_grad) {
+  extern __shared__ unsigned char smem_raw[];
+  int* s_rank = reinterpret_cast<int*>(smem_raw);
+  float* s_depth = reinterpret_cast<float*>(smem_raw) + (size_t)prm.d * kPixBlock;
+  float* s_dg = s_depth + (size_t)prm.d * kPixBlock;
+  int4* s_list = reinterpret_cast<int4*>(s_dg + (size_t)prm.d * kPixBlock);            // [8 warps][2 halves][d]
+  float* s_fg = reinterpret_cast<float*>(s_list + (size_t)kBwdWarps * 2 * prm.d);       // [c][33] (NCHW output only)
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int half = lane >> 4, hl = lane & 15;
+  const int c4 = prm.c >> 2;   // <= 16
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const int blk = blockIdx.x;
+  const int per_img = prm.blocks_w * prm.blocks_h;
+  const int bn = blk / per_img;
+  const int brem = blk - bn * per_img;
+  const int bh = brem / prm.blocks_w, bw = brem - bh * prm.blocks_w;
+  const int h0 = bh * kPixH, w0 = bw * kPixW;
+  const int64_t hw = (int64_t)prm.h * prm.w;
+  const int64_t img_base = (int64_t)bn * prm.d * hw;
+  pdl_wait();
+  {
+    const int px = threadIdx.x & 31;
+    const int hh = h0 + (px >> 3), ww = w0 + (px & 7);
+    const bool in = hh < prm.h && ww < prm.w;
+    const int64_t o0 = img_base + (int64_t)hh * prm.w + ww;
+    for (int dd = threadIdx.x >> 5; dd < prm.d; dd += kBwdWarps) {
+      int r = -1;
+      float dv = 0.f;
+      if (in) {
+        r = ldg_stream_i32(point_rank + o0 + dd * hw);
+        if (r >= 0) dv = Vec4<T>::load1(depth, o0 + dd * hw);
+      }
+      s_rank[dd * kPixBlock + px] = r;
+      s_depth[dd * kPixBlock + px] = dv;
+      s_dg[dd * kPixBlock + px] = 0.f;
+    }
+  }
+  __syncthreads();
+
+  int4* my_list = s_list + ((size_t)warp * 2 + half) * prm.d;
+  const bool act = hl < c4;
+  const int lane_c = 4 * min(hl, c4 - 1);     // idle lanes alias the last chunk; never stored
+  const T* og_lane = og + lane_c;
+  const unsigned hshift = 16u * half;
+  for (int it = 0; it < kPixBlock / (2 * kBwdWarps); ++it) {
+    const int px = it * 2 * kBwdWarps + 2 * warp + half;     // this half-warp's pixel
+    const int hh = h0 + (px >> 3), ww = w0 + (px & 7);
+    const bool pin = hh < prm.h && ww < prm.w;
+    const int64_t pix = (int64_t)bn * hw + (int64_t)hh * prm.w + ww;
+    int n_kept = 0;
+    for (int d0 = 0; d0 < prm.d; d0 += 16) {
+      const int dd = d0 + hl;
+      const int r = (pin && dd < prm.d) ? s_rank[dd * kPixBlock + px] : -1;
+      const unsigned live = (__ballot_sync(kFullMask, r >= 0) >> hshift) & 0xffffu;
+      if (r >= 0)
+        my_list[n_kept + __popc(live & ((1u << hl) - 1u))] = make_int4(r, __float_as_int(s_depth[dd * kPixBlock + px]), dd, 0);
+      n_kept += __popc(live);
+    }
+    __syncwarp();
+    const int n_max = max(__shfl_sync(kFullMask, n_kept, 0), __shfl_sync(kFullMask, n_kept, 16));
+    const float4 fv = pin ? Vec4<T>::load(feat, pix * prm.c + lane_c) : zero;
+    float4 fg = zero;
+    for (int b = 0; b < n_max; b += 8) {
+      float4 g[8];
+      float dv[8], pr[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        g[u] = zero;
+        dv[u] = 0.f;
+        if (b + u < n_kept) {                     // uniform within the half-warp
+          const int4 e = my_list[b + u];
+          g[u] = Vec4<T>::load(og_lane, (int64_t)e.x * prm.c);
+          dv[u] = __int_as_float(e.y);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        fg = fma4(g[u], dv[u], fg);
+        pr[u] = act ? dot4_packed(g[u], fv) : 0.f;
+      }
+      // reduce-scatter over lane bits 2,1,0, then bit 3 (stays inside the half-warp): lane hl ends up with the
+      // complete dot product of point b + (hl & 7)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float mine = (lane & 4) ? pr[u + 4] : pr[u];
+        const float send = (lane & 4) ? pr[u] : pr[u + 4];
+        pr[u] = mine + __shfl_xor_sync(kFullMask, send, 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float mine = (lane & 2) ? pr[u + 2] : pr[u];
+        const float send = (lane & 2) ? pr[u] : pr[u + 2];
+        pr[u] = mine + __shfl_xor_sync(kFullMask, send, 2);
+      }
+      {
+        const float mine = (lane & 1) ? pr[1] : pr[0];
+        const float send = (lane & 1) ? pr[0] : pr[1];
+        pr[0] = mine + __shfl_xor_sync(kFullMask, send, 1);
+      }
+      pr[0] += __shfl_xor_sync(kFullMask, pr[0], 8);
+      if (hl < 8 && b + hl < n_kept) s_dg[my_list[b + hl].z * kPixBlock + px] = pr[0];
+    }
+    __syncwarp();
+    if (prm.feat_grad_nchw) {
+      if (act && pin) {
+        float* c = s_fg + (4 * hl) * (kPixBlock + 1) + px;
+        c[0 * (kPixBlock + 1)] = fg.x;
+        c[1 * (kPixBlock + 1)] = fg.y;
+        c[2 * (kPixBlock + 1)] = fg.z;
+        c[3 * (kPixBlock + 1)] = fg.w;
+      }
+    } else if (act && pin) {
+      Vec4<T>::store(feat_grad, pix * prm.c + lane_c, fg);
+    }
+  }
+  __syncthreads();
+  const int px = threadIdx.x & 31;
+  const int hh = h0 + (px >> 3), ww = w0 + (px & 7);
+  if (hh < prm.h && ww < prm.w) {
+    if (prm.feat_grad_nchw) {
+      const int64_t o0 = (int64_t)bn * prm.c * hw + (int64_t)hh * prm.w + ww;
+      for (int cc = threadIdx.x >> 5; cc < prm.c; cc += kBwdWarps)
+        Vec4<T>::store1s(feat_grad, o0 + cc * hw, s_fg[cc * (kPixBlock + 1) + px]);
+    }
+    const int64_t o0 = img_base + (int64_t)hh * prm.w + ww;
+    for (int dd = threadIdx.x >> 5; dd < prm.d; dd += kBwdWarps)
+      Vec4<T>::store1s(depth_grad, o0 + dd * hw, s_dg[dd * kPixBlock + px]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ backward, joint columns
 // Same contract as pool_bwd_block_kernel, for grids where the pixels of one image column mostly land in the
 // same voxel at a given depth bin (Z == 1 BEV grids: the 4 pixels (h0..h0+3, w) of a warp's column differ only
@@ -1122,14 +1260,15 @@ static int backward_block_t(const void* og, void* dg, void* fg, const void* dept
   if (n_blocks == 0) return 0;
   if (n_blocks > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
   const int cw = prm.c < 128 ? prm.c : 128;
+  const bool half = prm.c <= 64;     // two pixels per warp
   const size_t smem = sizeof(float) * ((size_t)3 * prm.d * kPixBlock + (prm.feat_grad_nchw ? (size_t)cw * (kPixBlock + 1) : 0)) +
-                      sizeof(int4) * (size_t)kBwdWarps * prm.d;
+                      sizeof(int4) * (size_t)kBwdWarps * prm.d * (half ? 2 : 1);
   if (smem > 200 * 1024) return BEVPOOL_ERR_BAD_ARG;   // D > ~500 depth bins
-  auto kern = pool_bwd_block_kernel<T>;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
+  auto kern = half ? pool_bwd_block_half_kernel<T> : pool_bwd_block_kernel<T>;
+  static size_t attr[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > attr[half]) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = smem;
+    attr[half] = smem;
   }
   kern<<<(unsigned)n_blocks, kBwdThreads, smem, st>>>((const T*)og, (const T*)depth, (const T*)feat, point_rank, prm,
                                                        (T*)dg, (T*)fg);
