@@ -51,7 +51,12 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
                         const float* __restrict__ rots, const float* __restrict__ trans, ScatterParams prm,
                         int* __restrict__ point_rank, float* __restrict__ acc_grid) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int d_pad = (prm.d + 3) & ~3;
+  // Narrow rows (C <= 64 / C <= 32) would leave half / three quarters of the lanes idle: the warp is cut into G
+  // lane groups that walk the SAME column but interleaved depth bins (group g takes bins g, g + G, ...), each with
+  // its own accumulators. Branches are then uniform per group, not per warp (groups usually take the same path).
+  constexpr int G = (CH4 == 0 || CH4 > 16) ? 1 : (CH4 > 8 ? 2 : 4);
+  constexpr int LG = 32 / G;
+  const int d_pad = (prm.d + 4 * G - 1) / (4 * G) * (4 * G);
   int4* s_rank4 = reinterpret_cast<int4*>(smem_raw);                               // [d_pad][8]: ranks of rows h0..h0+3
   float4* s_depth4 = reinterpret_cast<float4*>(s_rank4 + (size_t)d_pad * kScW);    // [d_pad][8]
   int* s_lead = reinterpret_cast<int*>(s_depth4 + (size_t)d_pad * kScW);           // [d_pad][8]: see below
@@ -60,6 +65,7 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
   const int c4 = CH4 ? CH4 : (prm.c >> 2);
   const int C = 4 * c4;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int grp = lane / LG, sl = lane % LG;
 
   const int blk = blockIdx.x;
   const int per_img = prm.blocks_w * prm.blocks_h;
@@ -130,8 +136,8 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
 
   const int ww = w0 + warp;   // this warp's image column
   if (ww >= prm.w) return;    // warp-uniform; no barrier below
-  const bool act = lane < c4;
-  const int lane_c = 4 * (act ? lane : c4 - 1);   // idle lanes alias the last chunk; they never issue a RED
+  const bool act = sl < c4;
+  const int lane_c = 4 * (act ? sl : c4 - 1);   // idle lanes alias the last chunk; they never issue a RED
   float4 fv[kScH], acc[kScH];
   int cur[kScH];
 #pragma unroll
@@ -141,9 +147,9 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
     fv[p] = (h0 + p < prm.h) ? Vec4<T>::load(feat, ((int64_t)bn * hw + (h0 + p) * prm.w + ww) * C + lane_c) : zero;
   }
   float* grid_lane = acc_grid + lane_c;
-  const int4* rank_col = s_rank4 + warp;
-  const float4* depth_col = s_depth4 + warp;
-  const int* lead_col = s_lead + warp;
+  const int4* rank_col = s_rank4 + warp + grp * kScW;       // this lane group's first bin
+  const float4* depth_col = s_depth4 + warp + grp * kScW;
+  const int* lead_col = s_lead + warp + grp * kScW;
 
   // point (row p, rank rp, depth dp): join the accumulator holding voxel rp, else evict row p's accumulator
 #define BEVPOOL_SC_PUT(p, rp, dp)                                                        \
@@ -163,13 +169,13 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
   // every shared-memory access has an immediate offset. (Routing the summaries through a warp reduction to get
   // them into uniform registers removes the BSSY/BSYNC bookkeeping but CREDUX costs as much: measured equal.)
   int cur0 = -1;
-  for (int d0 = 0; d0 < prm.d; d0 += 4) {
+  for (int d0 = 0; d0 < d_pad; d0 += 4 * G) {
     int lead[4];
     float4 dp[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      lead[u] = lead_col[(d0 + u) * kScW];     // broadcast LDS
-      dp[u] = depth_col[(d0 + u) * kScW];      // broadcast LDS.128
+      lead[u] = lead_col[(d0 + G * u) * kScW];     // broadcast LDS (per lane group)
+      dp[u] = depth_col[(d0 + G * u) * kScW];      // broadcast LDS.128
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -190,7 +196,7 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
         continue;
       }
       cur[0] = cur0;
-      const int4 r = rank_col[(d0 + u) * kScW];
+      const int4 r = rank_col[(d0 + G * u) * kScW];
       BEVPOOL_SC_PUT(0, r.x, dp[u].x)
       BEVPOOL_SC_PUT(1, r.y, dp[u].y)
       BEVPOOL_SC_PUT(2, r.z, dp[u].z)
@@ -275,7 +281,7 @@ static int view_forward_t(const void* depth, const void* feat, const float* frus
   prm.blocks_h = (prm.h + kScH - 1) / kScH;
   const int64_t blocks = (int64_t)prm.bn * prm.blocks_w * prm.blocks_h;
   if (blocks > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
-  const size_t smem = (size_t)((prm.d + 3) & ~3) * kScW * (sizeof(int4) + sizeof(float4) + sizeof(int));
+  const size_t smem = (size_t)((prm.d + 15) & ~15) * kScW * (sizeof(int4) + sizeof(float4) + sizeof(int));
   if (smem > 200 * 1024) return BEVPOOL_ERR_BAD_ARG;
   if (blocks > 0) {
     switch (prm.c) {
