@@ -43,7 +43,51 @@ __device__ __forceinline__ void red_add_f32x4(float* p, float4 v) {
                : "memory");
 }
 
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ float4 mul4(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+
+// A lane's slice of a C-channel row: channels 4*sl .. 4*sl+3 and, in the "4 + 1" mapping used for C = 80
+// (X = true: 16 lanes x 5 channels, so two lane groups fit in a warp), also channel 64 + sl.
+template <bool X>
+struct Frag {
+  float4 v;
+  float s;
+};
+template <typename T, bool X>
+__device__ __forceinline__ Frag<X> frag_load(const T* row, int sl) {
+  Frag<X> f;
+  f.v = Vec4<T>::load(row, 4 * sl);
+  f.s = X ? Vec4<T>::load1(row, 64 + sl) : 0.f;
+  return f;
+}
+template <bool X>
+__device__ __forceinline__ Frag<X> frag_zero() {
+  Frag<X> f;
+  f.v = make_float4(0.f, 0.f, 0.f, 0.f);
+  f.s = 0.f;
+  return f;
+}
+template <bool X>
+__device__ __forceinline__ Frag<X> frag_fma(const Frag<X>& a, float d, Frag<X> acc) {
+  acc.v = fma4(a.v, d, acc.v);
+  if (X) acc.s = fmaf(a.s, d, acc.s);
+  return acc;
+}
+template <bool X>
+__device__ __forceinline__ Frag<X> frag_mul(const Frag<X>& a, float d) {
+  Frag<X> r;
+  r.v = mul4(a.v, d);
+  r.s = X ? a.s * d : 0.f;
+  return r;
+}
+template <bool X>
+__device__ __forceinline__ void frag_red(float* row, int sl, const Frag<X>& a) {
+  red_add_f32x4(row + 4 * sl, a.v);
+  if (X) red_add_f32(row + 64 + sl, a.s);
+}
 
 template <typename T, int CH4>
 __global__ void __launch_bounds__(kScThreads, 3)
@@ -54,7 +98,9 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
   // Narrow rows (C <= 64 / C <= 32) would leave half / three quarters of the lanes idle: the warp is cut into G
   // lane groups that walk the SAME column but interleaved depth bins (group g takes bins g, g + G, ...), each with
   // its own accumulators. Branches are then uniform per group, not per warp (groups usually take the same path).
-  constexpr int G = (CH4 == 0 || CH4 > 16) ? 1 : (CH4 > 8 ? 2 : 4);
+  // C = 80 uses the 4 + 1 channel mapping (Frag<true>): 16 lanes cover a row, so it also gets two groups.
+  constexpr bool X = CH4 == 20;
+  constexpr int G = X ? 2 : ((CH4 == 0 || CH4 > 16) ? 1 : (CH4 > 8 ? 2 : 4));
   constexpr int LG = 32 / G;
   const int d_pad = (prm.d + 4 * G - 1) / (4 * G) * (4 * G);
   int4* s_rank4 = reinterpret_cast<int4*>(smem_raw);                               // [d_pad][8]: ranks of rows h0..h0+3
@@ -136,17 +182,17 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
 
   const int ww = w0 + warp;   // this warp's image column
   if (ww >= prm.w) return;    // warp-uniform; no barrier below
-  const bool act = sl < c4;
-  const int lane_c = 4 * (act ? sl : c4 - 1);   // idle lanes alias the last chunk; they never issue a RED
-  float4 fv[kScH], acc[kScH];
+  const int rl = X ? 16 : c4;                  // lanes a row occupies
+  const bool act = sl < rl;
+  const int sc = act ? sl : rl - 1;            // idle lanes alias the last slice; they never issue a RED
+  Frag<X> fv[kScH], acc[kScH];
   int cur[kScH];
 #pragma unroll
   for (int p = 0; p < kScH; ++p) {
-    acc[p] = zero;
+    acc[p] = frag_zero<X>();
     cur[p] = -1;
-    fv[p] = (h0 + p < prm.h) ? Vec4<T>::load(feat, ((int64_t)bn * hw + (h0 + p) * prm.w + ww) * C + lane_c) : zero;
+    fv[p] = (h0 + p < prm.h) ? frag_load<T, X>(feat + ((int64_t)bn * hw + (h0 + p) * prm.w + ww) * C, sc) : frag_zero<X>();
   }
-  float* grid_lane = acc_grid + lane_c;
   const int4* rank_col = s_rank4 + warp + grp * kScW;       // this lane group's first bin
   const float4* depth_col = s_depth4 + warp + grp * kScW;
   const int* lead_col = s_lead + warp + grp * kScW;
@@ -154,14 +200,14 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
   // point (row p, rank rp, depth dp): join the accumulator holding voxel rp, else evict row p's accumulator
 #define BEVPOOL_SC_PUT(p, rp, dp)                                                        \
   if ((rp) >= 0) {                                                                       \
-    if ((rp) == cur[0]) acc[0] = fma4(fv[p], (dp), acc[0]);                              \
-    else if ((rp) == cur[1]) acc[1] = fma4(fv[p], (dp), acc[1]);                         \
-    else if ((rp) == cur[2]) acc[2] = fma4(fv[p], (dp), acc[2]);                         \
-    else if ((rp) == cur[3]) acc[3] = fma4(fv[p], (dp), acc[3]);                         \
+    if ((rp) == cur[0]) acc[0] = frag_fma<X>(fv[p], (dp), acc[0]);                       \
+    else if ((rp) == cur[1]) acc[1] = frag_fma<X>(fv[p], (dp), acc[1]);                  \
+    else if ((rp) == cur[2]) acc[2] = frag_fma<X>(fv[p], (dp), acc[2]);                  \
+    else if ((rp) == cur[3]) acc[3] = frag_fma<X>(fv[p], (dp), acc[3]);                  \
     else {                                                                               \
-      if (cur[p] >= 0 && act) red_add_f32x4(grid_lane + (int64_t)cur[p] * C, acc[p]);    \
+      if (cur[p] >= 0 && act) frag_red<X>(acc_grid + (int64_t)cur[p] * C, sc, acc[p]);   \
       cur[p] = (rp);                                                                     \
-      acc[p] = mul4(fv[p], (dp));                                                        \
+      acc[p] = frag_mul<X>(fv[p], (dp));                                                 \
     }                                                                                    \
   }
 
@@ -185,14 +231,14 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
         // fast path (every bin of a Z == 1 grid, most bins otherwise): all kept rows of the column share ONE
         // voxel. One comparison against the open accumulator, four unconditional FMAs (dropped rows weigh 0).
         if (lu != cur0) {
-          if (cur0 >= 0 && act) red_add_f32x4(grid_lane + (int64_t)cur0 * C, acc[0]);
+          if (cur0 >= 0 && act) frag_red<X>(acc_grid + (int64_t)cur0 * C, sc, acc[0]);
           cur0 = lu;
-          acc[0] = zero;
+          acc[0] = frag_zero<X>();
         }
-        acc[0] = fma4(fv[0], dp[u].x, acc[0]);
-        acc[0] = fma4(fv[1], dp[u].y, acc[0]);
-        acc[0] = fma4(fv[2], dp[u].z, acc[0]);
-        acc[0] = fma4(fv[3], dp[u].w, acc[0]);
+        acc[0] = frag_fma<X>(fv[0], dp[u].x, acc[0]);
+        acc[0] = frag_fma<X>(fv[1], dp[u].y, acc[0]);
+        acc[0] = frag_fma<X>(fv[2], dp[u].z, acc[0]);
+        acc[0] = frag_fma<X>(fv[3], dp[u].w, acc[0]);
         continue;
       }
       cur[0] = cur0;
@@ -209,7 +255,7 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
   if (act) {
 #pragma unroll
     for (int p = 0; p < kScH; ++p)
-      if (cur[p] >= 0) red_add_f32x4(grid_lane + (int64_t)cur[p] * C, acc[p]);
+      if (cur[p] >= 0) frag_red<X>(acc_grid + (int64_t)cur[p] * C, sc, acc[p]);
   }
 }
 
