@@ -219,6 +219,49 @@ __device__ __forceinline__ uint32_t lookback_exclusive(uint32_t* status, int64_t
   return excl;
 }
 
+// ------------------------------------------------------------------------------------------ row fragments
+__device__ __forceinline__ float4 mul4(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+
+// A lane's slice of a C-channel row: channels 4*sl .. 4*sl+3 and, in the "4 + 1" mapping used for C = 80
+// (X = true: 16 lanes x 5 channels, so two lane groups fit in a warp), also channel 64 + sl.
+template <bool X>
+struct Frag {
+  float4 v;
+  float s;
+};
+template <typename T, bool X>
+__device__ __forceinline__ Frag<X> frag_load(const T* row, int sl) {
+  Frag<X> f;
+  f.v = Vec4<T>::load(row, 4 * sl);
+  f.s = X ? Vec4<T>::load1(row, 64 + sl) : 0.f;
+  return f;
+}
+template <bool X>
+__device__ __forceinline__ Frag<X> frag_zero() {
+  Frag<X> f;
+  f.v = make_float4(0.f, 0.f, 0.f, 0.f);
+  f.s = 0.f;
+  return f;
+}
+template <bool X>
+__device__ __forceinline__ Frag<X> frag_fma(const Frag<X>& a, float d, Frag<X> acc) {
+  acc.v = fma4(a.v, d, acc.v);
+  if (X) acc.s = fmaf(a.s, d, acc.s);
+  return acc;
+}
+template <bool X>
+__device__ __forceinline__ Frag<X> frag_mul(const Frag<X>& a, float d) {
+  Frag<X> r;
+  r.v = mul4(a.v, d);
+  r.s = X ? a.s * d : 0.f;
+  return r;
+}
+template <bool X>
+__device__ __forceinline__ float frag_dot(const Frag<X>& a, const Frag<X>& b) {
+  const float d = dot4_packed(a.v, b.v);
+  return X ? fmaf(a.s, b.s, d) : d;
+}
+
 // ------------------------------------------------------------------------------------------ geometry
 // Exactness (SURVEY.md §7 hard part 3): r0*x + r1*y + r2*z + t with every product and sum rounded separately,
 // voxel index = trunc((coor - lo) / dx) with an IEEE fp32 subtract and divide (no reciprocal, no FMA).

@@ -960,17 +960,23 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
   if (g_fwd_timeline_on && threadIdx.x == 0) t_a = globaltimer_ns();
 
   const int ww = w0 + warp;   // this warp's image column
-  const bool act = lane < CH4;
-  const int lane_c = 4 * (act ? lane : CH4 - 1);          // idle lanes alias the last chunk; never stored
-  const T* og_lane = og + lane_c;
-  constexpr int PS = C + 4;   // partial-row stride: (20*k + p + 4*l) mod 32 is conflict-free for the transposed read
-  float* my_part = s_part + (size_t)warp * kJointBins * PS + lane_c;
-  float4 fv[kPixH], fg[kPixH];
+  // C = 80 uses the 4 + 1 channel mapping (Frag<true>: lane sl holds channels 4sl..4sl+3 and 64+sl), so a row is 16
+  // lanes wide and the warp splits into two lane groups that take alternating bins of the 8-bin window.
+  constexpr bool X = CH4 == 20;
+  constexpr int G = X ? 2 : 1;
+  constexpr int RL = X ? 16 : CH4;          // lanes per row
+  constexpr int NU = 4 / G;                 // bins per group and pass
+  const int grp = lane / (32 / G), sl = lane % (32 / G);
+  const bool act = sl < RL;
+  const int sc = act ? sl : RL - 1;         // idle lanes alias the last slice; never stored
+  constexpr int PS = 4 * RL + 4;   // partial-row stride: (4k + p + 4l) mod 32 is conflict-free for the transposed read
+  float* my_part = s_part + (size_t)warp * kJointBins * PS + 4 * sc;
+  Frag<X> fv[kPixH], fg[kPixH];
 #pragma unroll
   for (int p = 0; p < kPixH; ++p) {
-    fg[p] = zero;
-    fv[p] = (ww < prm.w && h0 + p < prm.h)
-                ? Vec4<T>::load(feat, ((int64_t)bn * hw + (h0 + p) * prm.w + ww) * C + lane_c) : zero;
+    fg[p] = frag_zero<X>();
+    fv[p] = (ww < prm.w && h0 + p < prm.h) ? frag_load<T, X>(feat + ((int64_t)bn * hw + (h0 + p) * prm.w + ww) * C, sc)
+                                           : frag_zero<X>();
   }
   if (ww < prm.w) {   // warp-uniform
     const int4* rank_col = s_rank4 + warp;
@@ -979,47 +985,53 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
     for (int d0 = 0; d0 < prm.d; d0 += kJointBins) {
 #pragma unroll
       for (int k0 = 0; k0 < kJointBins; k0 += 4) {
-        // 4 bins at a time: lead rows requested first, then consumed (the summaries are identical in all lanes)
-        int code[4];
-        float4 g[4];
+        // NU bins per lane group at a time (bins k0 + G*u + grp): lead rows requested first, then consumed
+        int code[NU];
+        Frag<X> g[NU];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          code[u] = lead_col[(d0 + k0 + u) * kPixW];   // broadcast LDS
-          g[u] = zero;
-          if (code[u] != -1) g[u] = Vec4<T>::load(og_lane, (int64_t)(code[u] >= 0 ? code[u] : -2 - code[u]) * C);
+        for (int u = 0; u < NU; ++u) {
+          code[u] = lead_col[(d0 + k0 + G * u + grp) * kPixW];   // broadcast LDS (per lane group)
+          g[u] = frag_zero<X>();
+          if (code[u] != -1) g[u] = frag_load<T, X>(og + (int64_t)(code[u] >= 0 ? code[u] : -2 - code[u]) * C, sc);
         }
-        const int cmax = max(max(code[0], code[1]), max(code[2], code[3]));
-        const int cmin = min(min(code[0], code[1]), min(code[2], code[3]));
-        if (cmax == -1) continue;   // warp-uniform: the 4 bins are empty (dropped points come in long runs)
+        int cmax = code[0], cmin = code[0];
+#pragma unroll
+        for (int u = 1; u < NU; ++u) {
+          cmax = max(cmax, code[u]);
+          cmin = min(cmin, code[u]);
+        }
+        if (cmax == -1) continue;   // group-uniform: the bins are empty (dropped points come in long runs)
         if (cmin >= -1) {
-          // no mixed column among the 4 bins: straight-line code, no per-bin branches. Empty bins ride along with
+          // no mixed column among the bins: straight-line code, no per-bin branches. Empty bins ride along with
           // g = 0 and weights 0 (their partials are discarded by the reducing lane below).
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float4 dp = depth_col[(d0 + k0 + u) * kPixW];
+          for (int u = 0; u < NU; ++u) {
+            const int k = k0 + G * u + grp;
+            const float4 dp = depth_col[(d0 + k) * kPixW];
             const float dw[kPixH] = {dp.x, dp.y, dp.z, dp.w};
             float dt[kPixH];
 #pragma unroll
             for (int p = 0; p < kPixH; ++p) {
-              fg[p] = fma4(g[u], dw[p], fg[p]);
-              dt[p] = dot4_packed(g[u], fv[p]);
+              fg[p] = frag_fma<X>(g[u], dw[p], fg[p]);
+              dt[p] = frag_dot<X>(g[u], fv[p]);
             }
-            if (act) *reinterpret_cast<float4*>(my_part + (k0 + u) * PS) = make_float4(dt[0], dt[1], dt[2], dt[3]);
+            if (act) *reinterpret_cast<float4*>(my_part + k * PS) = make_float4(dt[0], dt[1], dt[2], dt[3]);
           }
           continue;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NU; ++u) {
           if (code[u] == -1) continue;
-          const int dd = d0 + k0 + u;
+          const int k = k0 + G * u + grp;
+          const int dd = d0 + k;
           const float4 dp = depth_col[dd * kPixW];
           const float dw[kPixH] = {dp.x, dp.y, dp.z, dp.w};
           float dt[kPixH];
           if (code[u] >= 0) {   // every kept pixel of the column sits in the lead voxel; dropped rows weigh 0
 #pragma unroll
             for (int p = 0; p < kPixH; ++p) {
-              fg[p] = fma4(g[u], dw[p], fg[p]);
-              dt[p] = dot4_packed(g[u], fv[p]);   // dropped rows: discarded by the reducing lane below
+              fg[p] = frag_fma<X>(g[u], dw[p], fg[p]);
+              dt[p] = frag_dot<X>(g[u], fv[p]);   // dropped rows: discarded by the reducing lane below
             }
           } else {
             // mixed column: rows of one voxel are adjacent (height is monotonic along the column), so a row is
@@ -1027,7 +1039,7 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
             const int lead = -2 - code[u];
             const int4 r4 = rank_col[dd * kPixW];
             const int rr[kPixH] = {r4.x, r4.y, r4.z, r4.w};
-            float4 gp = g[u];
+            Frag<X> gp = g[u];
             int rp = lead;
 #pragma unroll
             for (int p = 0; p < kPixH; ++p) {
@@ -1035,18 +1047,19 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
               if (rr[p] >= 0) {
                 if (rr[p] != rp) {
                   rp = rr[p];
-                  gp = rp == lead ? g[u] : Vec4<T>::load(og_lane, (int64_t)rp * C);
+                  if (rp == lead) gp = g[u];
+                  else gp = frag_load<T, X>(og + (int64_t)rp * C, sc);
                 }
-                fg[p] = fma4(gp, dw[p], fg[p]);
-                dt[p] = dot4_packed(gp, fv[p]);
+                fg[p] = frag_fma<X>(gp, dw[p], fg[p]);
+                dt[p] = frag_dot<X>(gp, fv[p]);
               }
             }
           }
-          if (act) *reinterpret_cast<float4*>(my_part + (k0 + u) * PS) = make_float4(dt[0], dt[1], dt[2], dt[3]);
+          if (act) *reinterpret_cast<float4*>(my_part + k * PS) = make_float4(dt[0], dt[1], dt[2], dt[3]);
         }
       }
       __syncwarp();
-      // ---- lane (k, p) sums the CH4 partial dot products of bin d0 + k, pixel p
+      // ---- lane (k, p) sums the RL partial dot products of bin d0 + k, pixel p
       {
         const int k = lane >> 2, pz = lane & 3;
         const int dd = d0 + k;
@@ -1056,7 +1069,7 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
           if (mine >= 0) {
             const float* src = s_part + (size_t)warp * kJointBins * PS + k * PS + pz;
 #pragma unroll
-            for (int l = 0; l < CH4; ++l) sum += src[4 * l];
+            for (int l = 0; l < RL; ++l) sum += src[4 * l];
           }
           reinterpret_cast<float*>(s_dg4 + dd * kPixW + warp)[pz] = sum;
         }
@@ -1066,17 +1079,29 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
   } else {
     for (int d = lane; d < prm.d; d += 32) s_dg4[d * kPixW + warp] = zero;
   }
+  if (G == 2) {   // the two lane groups hold feat_grad of alternating bins: add them up, group 0 stores
+#pragma unroll
+    for (int p = 0; p < kPixH; ++p) {
+      fg[p].v.x += __shfl_xor_sync(kFullMask, fg[p].v.x, 16);
+      fg[p].v.y += __shfl_xor_sync(kFullMask, fg[p].v.y, 16);
+      fg[p].v.z += __shfl_xor_sync(kFullMask, fg[p].v.z, 16);
+      fg[p].v.w += __shfl_xor_sync(kFullMask, fg[p].v.w, 16);
+      fg[p].s += __shfl_xor_sync(kFullMask, fg[p].s, 16);
+    }
+  }
+  const bool writer = act && grp == 0;
   // ---- feat_grad of the 4 pixels
   if (prm.feat_grad_nchw) {
     __syncthreads();   // every warp is done with its partial buffer: re-use it as the transpose tile
-    if (ww < prm.w && act) {
+    if (ww < prm.w && writer) {
 #pragma unroll
       for (int p = 0; p < kPixH; ++p) {
-        float* c = s_fg + lane_c * kJointPad + p * kPixW + warp;
-        c[0 * kJointPad] = fg[p].x;
-        c[1 * kJointPad] = fg[p].y;
-        c[2 * kJointPad] = fg[p].z;
-        c[3 * kJointPad] = fg[p].w;
+        float* c = s_fg + (4 * sc) * kJointPad + p * kPixW + warp;
+        c[0 * kJointPad] = fg[p].v.x;
+        c[1 * kJointPad] = fg[p].v.y;
+        c[2 * kJointPad] = fg[p].v.z;
+        c[3 * kJointPad] = fg[p].v.w;
+        if (X) s_fg[(64 + sc) * kJointPad + p * kPixW + warp] = fg[p].s;
       }
     }
     __syncthreads();
@@ -1086,10 +1111,14 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
       for (int cc = warp; cc < C; cc += kBwdWarps)
         Vec4<T>::store1s(feat_grad, o0 + (int64_t)cc * hw, s_fg[cc * kJointPad + lane]);
     }
-  } else if (ww < prm.w && act) {
+  } else if (ww < prm.w && writer) {
 #pragma unroll
     for (int p = 0; p < kPixH; ++p)
-      if (h0 + p < prm.h) Vec4<T>::store(feat_grad, ((int64_t)bn * hw + (h0 + p) * prm.w + ww) * C + lane_c, fg[p]);
+      if (h0 + p < prm.h) {
+        const int64_t o = ((int64_t)bn * hw + (h0 + p) * prm.w + ww) * C;
+        Vec4<T>::store(feat_grad, o + 4 * sc, fg[p].v);
+        if (X) Vec4<T>::store1(feat_grad, o + 64 + sc, fg[p].s);
+      }
   }
   __syncthreads();
   if (g_fwd_timeline_on && threadIdx.x == 0) t_b = globaltimer_ns();
@@ -1212,7 +1241,7 @@ template <typename T, int CH4>
 static int backward_joint_launch(const void* og, void* dg, void* fg, const void* depth, const void* feat,
                                  const int* point_rank, const BwdParams& prm, int64_t n_blocks, cudaStream_t st) {
   constexpr int C = CH4 * 4;
-  size_t part_bytes = sizeof(float) * (size_t)kBwdWarps * kJointBins * (C + 4);
+  size_t part_bytes = sizeof(float) * (size_t)kBwdWarps * kJointBins * (C + 4);   // >= 4 * RL + 4 per bin
   const size_t fg_bytes = prm.feat_grad_nchw ? sizeof(float) * (size_t)C * kJointPad : 0;
   if (fg_bytes > part_bytes) part_bytes = fg_bytes;
   const size_t d_pad = (size_t)(prm.d + kJointBins - 1) / kJointBins * kJointBins;
