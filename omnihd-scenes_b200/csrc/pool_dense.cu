@@ -963,7 +963,7 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
   // C = 80 uses the 4 + 1 channel mapping (Frag<true>: lane sl holds channels 4sl..4sl+3 and 64+sl), so a row is 16
   // lanes wide and the warp splits into two lane groups that take alternating bins of the 8-bin window.
   constexpr bool X = CH4 == 20;
-  constexpr int G = X ? 2 : 1;
+  constexpr int G = X ? 2 : (CH4 <= 8 ? 4 : (CH4 <= 16 ? 2 : 1));   // narrow rows: more groups
   constexpr int RL = X ? 16 : CH4;          // lanes per row
   constexpr int NU = 4 / G;                 // bins per group and pass
   const int grp = lane / (32 / G), sl = lane % (32 / G);
@@ -1079,14 +1079,16 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
   } else {
     for (int d = lane; d < prm.d; d += 32) s_dg4[d * kPixW + warp] = zero;
   }
-  if (G == 2) {   // the two lane groups hold feat_grad of alternating bins: add them up, group 0 stores
+  // the lane groups hold feat_grad of interleaved bins: add them up, group 0 stores
+#pragma unroll
+  for (int o = 16; o >= 32 / G && G > 1; o >>= 1) {
 #pragma unroll
     for (int p = 0; p < kPixH; ++p) {
-      fg[p].v.x += __shfl_xor_sync(kFullMask, fg[p].v.x, 16);
-      fg[p].v.y += __shfl_xor_sync(kFullMask, fg[p].v.y, 16);
-      fg[p].v.z += __shfl_xor_sync(kFullMask, fg[p].v.z, 16);
-      fg[p].v.w += __shfl_xor_sync(kFullMask, fg[p].v.w, 16);
-      fg[p].s += __shfl_xor_sync(kFullMask, fg[p].s, 16);
+      fg[p].v.x += __shfl_xor_sync(kFullMask, fg[p].v.x, o);
+      fg[p].v.y += __shfl_xor_sync(kFullMask, fg[p].v.y, o);
+      fg[p].v.z += __shfl_xor_sync(kFullMask, fg[p].v.z, o);
+      fg[p].v.w += __shfl_xor_sync(kFullMask, fg[p].v.w, o);
+      if (X) fg[p].s += __shfl_xor_sync(kFullMask, fg[p].s, o);
     }
   }
   const bool writer = act && grp == 0;

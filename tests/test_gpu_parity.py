@@ -664,3 +664,27 @@ def test_pillar_scatter_vs_oracle(pkg, orc, B, C, ny, nx, P, dt):
         assert np.array_equal(out2.detach().float().cpu().numpy(), orc.pillar_scatter(fin[keep], bad[keep], B, ny, nx))
         out2.backward(gt)
         assert float(f2.grad[0].abs().max()) == 0.0 and float(f2.grad[-1].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("C", [4, 32, 64, 128])
+def test_fused_path_channel_counts_z1(pkg, orc, C):
+    """Z = 1 grid with the channel counts that select the other lane mappings of the fused kernels (C <= 32: four lane
+    groups, C <= 64: two, C = 128: one full-width group, C = 4: the generic block backward), fwd + bwd vs the oracle."""
+    import dataclasses
+    cfg = dataclasses.replace(pkg.synthetic.CONFIGS["bevdet_r50_b8"], channels=C)
+    B = 2
+    view, rots, trans, coor, (rb, rd, rf, st, ln), depth, feat, gout = synth_pool_case(pkg, orc, cfg, B, seed=5)
+    X, Y, Z = (int(v) for v in view.nx)
+    feat_cl = feat.permute(0, 1, 3, 4, 2).contiguous().numpy()
+    ref = orc.bev_pool_v2_forward(depth.numpy(), feat_cl, rd, rf, rb, (B, Z, Y, X, C), st, ln, exact=True)
+    gd, gf = orc.bev_pool_v2_backward(gout.permute(0, 2, 3, 4, 1).contiguous().numpy(), depth.numpy(), feat_cl,
+                                      rd, rf, rb, exact=True)
+    view = view.to(DEV)
+    for det in (False, True):
+        view.deterministic = det
+        d, f = depth.to(DEV).requires_grad_(), feat.to(DEV).requires_grad_()
+        bev = view(d, f, rots.to(DEV), trans.to(DEV))
+        assert rel_to_max(bev.detach().permute(0, 2, 3, 4, 1).cpu().numpy(), ref) <= TOL
+        bev.backward(gout.to(DEV))
+        assert rel_to_max(d.grad.cpu().numpy(), gd) <= TOL
+        assert rel_to_max(f.grad.permute(0, 1, 3, 4, 2).cpu().numpy(), gf) <= TOL
