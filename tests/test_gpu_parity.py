@@ -688,3 +688,28 @@ def test_fused_path_channel_counts_z1(pkg, orc, C):
         bev.backward(gout.to(DEV))
         assert rel_to_max(d.grad.cpu().numpy(), gd) <= TOL
         assert rel_to_max(f.grad.permute(0, 1, 3, 4, 2).cpu().numpy(), gf) <= TOL
+
+
+@pytest.mark.parametrize("zb,C", [((-5.0, 3.0, 8.0), 80), ((-3.0, 5.0, 0.5), 64), ((-3.0, 5.0, 2.0), 12)])
+def test_fused_path_ragged_feature_map(pkg, orc, zb, C):
+    """Feature map 5 x 13 (neither a multiple of the 4 x 8 pixel block), D = 7 (padded bins), one camera: partial
+    blocks, pad bins and idle warps of the scatter forward / joint / block backward kernels, vs the oracle."""
+    cfg = pkg.synthetic.ViewConfig("ragged", (80, 208), 16, (1.0, 29.0, 4.0), (-25.6, 25.6, 0.8), (-25.6, 25.6, 0.8), zb, C, 3,
+                                   n_cams=1)
+    B = 3
+    view, rots, trans, coor, (rb, rd, rf, st, ln), depth, feat, gout = synth_pool_case(pkg, orc, cfg, B, seed=8)
+    assert (view.fH, view.fW, view.D) == (5, 13, 7)
+    X, Y, Z = (int(v) for v in view.nx)
+    feat_cl = feat.permute(0, 1, 3, 4, 2).contiguous().numpy()
+    ref = orc.bev_pool_v2_forward(depth.numpy(), feat_cl, rd, rf, rb, (B, Z, Y, X, C), st, ln, exact=True)
+    gd, gf = orc.bev_pool_v2_backward(gout.permute(0, 2, 3, 4, 1).contiguous().numpy(), depth.numpy(), feat_cl,
+                                      rd, rf, rb, exact=True)
+    view = view.to(DEV)
+    for det in (False, True):
+        view.deterministic = det
+        d, f = depth.to(DEV).requires_grad_(), feat.to(DEV).requires_grad_()
+        bev = view(d, f, rots.to(DEV), trans.to(DEV))
+        assert rel_to_max(bev.detach().permute(0, 2, 3, 4, 1).cpu().numpy(), ref) <= TOL
+        bev.backward(gout.to(DEV))
+        assert rel_to_max(d.grad.cpu().numpy(), gd) <= TOL
+        assert rel_to_max(f.grad.permute(0, 1, 3, 4, 2).cpu().numpy(), gf) <= TOL
