@@ -103,7 +103,6 @@ struct Vec4<float> {
   static __device__ __forceinline__ void store_keep(float* base, int64_t elem, float4 v) {
     *reinterpret_cast<float4*>(base + elem) = v;
   }
-  static __device__ __forceinline__ float4 load_smem(const float* p) { return *reinterpret_cast<const float4*>(p); }
   static __device__ __forceinline__ float load1(const float* base, int64_t elem) { return __ldg(base + elem); }
   static __device__ __forceinline__ void store1(float* base, int64_t elem, float v) { base[elem] = v; }
   static __device__ __forceinline__ void store1s(float* base, int64_t elem, float v) { stg_stream_f32(base + elem, v); }
@@ -181,42 +180,6 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
   return v;
-}
-
-// ---- decoupled look-back on one 32-bit word: [31:30] flag, [29:0] value ----------------------
-constexpr uint32_t kFlagAggregate = 1u << 30;
-constexpr uint32_t kFlagPrefix = 2u << 30;
-constexpr uint32_t kValueMask = (1u << 30) - 1;
-
-__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_gpu(uint32_t* p, uint32_t v) {
-  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// status[t * stride] belongs to tile t. Returns the exclusive prefix of `aggregate` over tiles < tile.
-// The word carries flag and value together, so no fence is required.
-__device__ __forceinline__ uint32_t lookback_exclusive(uint32_t* status, int64_t stride, int tile,
-                                                       uint32_t aggregate) {
-  if (tile == 0) {
-    st_relaxed_gpu(status, kFlagPrefix | aggregate);
-    return 0;
-  }
-  st_relaxed_gpu(status + (int64_t)tile * stride, kFlagAggregate | aggregate);
-  uint32_t excl = 0;
-  for (int t = tile - 1; t >= 0; --t) {
-    uint32_t s;
-    do {
-      s = ld_relaxed_gpu(status + (int64_t)t * stride);
-    } while ((s >> 30) == 0);
-    excl += s & kValueMask;
-    if (s & kFlagPrefix) break;
-  }
-  st_relaxed_gpu(status + (int64_t)tile * stride, kFlagPrefix | ((excl + aggregate) & kValueMask));
-  return excl;
 }
 
 // ------------------------------------------------------------------------------------------ row fragments
