@@ -54,7 +54,10 @@ __device__ __forceinline__ void frag_red(float* row, int sl, const Frag<X>& a) {
   if (X) red_add_f32(row + 64 + sl, a.s);
 }
 
-template <typename T, int CH4>
+// HALVES = 2: the CTA covers 4 columns instead of 8 and two warps share a column, each walking half of the depth range
+// (nothing to combine: both push REDs). Warps then live half as long, which halves the idle tail of the last wave —
+// used when the launch is only a few waves long (cfg 2: 2.6 waves, 21 % of the SM-cycles were idle).
+template <typename T, int CH4, int HALVES>
 __global__ void __launch_bounds__(kScThreads, 3)
 view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat, const float* __restrict__ frustum,
                         const float* __restrict__ rots, const float* __restrict__ trans, ScatterParams prm,
@@ -67,10 +70,12 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
   constexpr bool X = CH4 == 20;
   constexpr int G = X ? 2 : ((CH4 == 0 || CH4 > 16) ? 1 : (CH4 > 8 ? 2 : 4));
   constexpr int LG = 32 / G;
-  const int d_pad = (prm.d + 4 * G - 1) / (4 * G) * (4 * G);
-  int4* s_rank4 = reinterpret_cast<int4*>(smem_raw);                               // [d_pad][8]: ranks of rows h0..h0+3
-  float4* s_depth4 = reinterpret_cast<float4*>(s_rank4 + (size_t)d_pad * kScW);    // [d_pad][8]
-  int* s_lead = reinterpret_cast<int*>(s_depth4 + (size_t)d_pad * kScW);           // [d_pad][8]: see below
+  constexpr int WB = kScW / HALVES;         // columns per CTA
+  constexpr int DQ = 4 * G * HALVES;        // bins are padded so every warp walks whole 4-bin groups per lane group
+  const int d_pad = (prm.d + DQ - 1) / DQ * DQ;
+  int4* s_rank4 = reinterpret_cast<int4*>(smem_raw);                             // [d_pad][WB]: ranks of rows h0..h0+3
+  float4* s_depth4 = reinterpret_cast<float4*>(s_rank4 + (size_t)d_pad * WB);    // [d_pad][WB]
+  int* s_lead = reinterpret_cast<int*>(s_depth4 + (size_t)d_pad * WB);           // [d_pad][WB]: see below
   __shared__ float s_cam[12];
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const int c4 = CH4 ? CH4 : (prm.c >> 2);
@@ -83,7 +88,7 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
   const int bn = blk / per_img;
   const int brem = blk - bn * per_img;
   const int bh = brem / prm.blocks_w, bw = brem - bh * prm.blocks_w;
-  const int h0 = bh * kScH, w0 = bw * kScW;
+  const int h0 = bh * kScH, w0 = bw * WB;
   const int hw = prm.h * prm.w;
   const int64_t img_base = (int64_t)bn * prm.d * hw;
   pdl_wait();
@@ -92,23 +97,26 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
       s_cam[threadIdx.x] = threadIdx.x < 9 ? __ldg(rots + bn * 9 + threadIdx.x) : __ldg(trans + bn * 3 + threadIdx.x - 9);
     __syncthreads();
   }
-  // ---- stage ranks / depths of the block: 8 consecutive w = one 32-byte sector per (d, h)
-  if (threadIdx.x < (d_pad - prm.d) * kScW) {
-    s_lead[prm.d * kScW + threadIdx.x] = -1;
-    s_depth4[prm.d * kScW + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // ---- stage ranks / depths of the block: WB consecutive w per (d, h) (8: one 32-byte sector); a warp covers
+  //      32 / (4 * WB) bins per pass
+  for (int i = threadIdx.x; i < (d_pad - prm.d) * WB; i += kScThreads) {
+    s_lead[prm.d * WB + i] = -1;
+    s_depth4[prm.d * WB + i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   {
-    const int hl = lane >> 3, wl = lane & 7;
+    constexpr int BPI = 32 / (4 * WB);        // bins per warp and pass
+    const int wl = lane % WB, hl = (lane / WB) & 3, bs = lane / (4 * WB);
+    const unsigned colmask = (WB == 8 ? 0x01010101u : 0x00001111u) << (wl + 4 * WB * bs);
     const bool in = h0 + hl < prm.h && w0 + wl < prm.w;
     const int pix = (h0 + hl) * prm.w + w0 + wl;
     const int64_t vpf = (int64_t)prm.nx * prm.ny * prm.nz;
     const int64_t frame_base = (int64_t)(bn / prm.n_cams) * vpf;
-    for (int d0 = 0; d0 < prm.d; d0 += 4 * kScWarps) {
+    for (int d0 = 0; d0 < prm.d; d0 += 4 * kScWarps * BPI) {
       int r[4];
       float dv[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int dd = d0 + k * kScWarps + warp;
+        const int dd = d0 + (k * kScWarps + warp) * BPI + bs;
         r[k] = -1;
         dv[k] = 0.f;
         if (in && dd < prm.d) {
@@ -129,24 +137,26 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int dd = d0 + k * kScWarps + warp;
+        const int dd = d0 + (k * kScWarps + warp) * BPI + bs;
         // column summary for the walk: -1 nothing kept, rank >= 0 all kept rows share that voxel, -2 mixed
-        int lead = max(r[k], __shfl_xor_sync(kFullMask, r[k], 8));
-        lead = max(lead, __shfl_xor_sync(kFullMask, lead, 16));
+        int lead = max(r[k], __shfl_xor_sync(kFullMask, r[k], WB));
+        lead = max(lead, __shfl_xor_sync(kFullMask, lead, 2 * WB));
         const unsigned agree = __ballot_sync(kFullMask, r[k] < 0 || r[k] == lead);
-        const bool shared = ((agree >> wl) & 0x01010101u) == 0x01010101u;
+        const bool shared = (agree & colmask) == colmask;
         if (dd < prm.d) {
-          reinterpret_cast<int*>(s_rank4 + dd * kScW + wl)[hl] = r[k];
-          reinterpret_cast<float*>(s_depth4 + dd * kScW + wl)[hl] = r[k] >= 0 ? dv[k] : 0.f;   // dropped: weight 0
-          if (hl == 0) s_lead[dd * kScW + wl] = lead < 0 ? -1 : (shared ? lead : -2);
+          reinterpret_cast<int*>(s_rank4 + dd * WB + wl)[hl] = r[k];
+          reinterpret_cast<float*>(s_depth4 + dd * WB + wl)[hl] = r[k] >= 0 ? dv[k] : 0.f;   // dropped: weight 0
+          if (hl == 0) s_lead[dd * WB + wl] = lead < 0 ? -1 : (shared ? lead : -2);
         }
       }
     }
   }
   __syncthreads();
 
-  const int ww = w0 + warp;   // this warp's image column
+  const int wcol = warp % WB, half = warp / WB;
+  const int ww = w0 + wcol;   // this warp's image column
   if (ww >= prm.w) return;    // warp-uniform; no barrier below
+  const int d_lo = half * (d_pad / HALVES), d_hi = d_lo + d_pad / HALVES;   // this warp's share of the depth range
   const int rl = X ? 16 : c4;                  // lanes a row occupies
   const bool act = sl < rl;
   const int sc = act ? sl : rl - 1;            // idle lanes alias the last slice; they never issue a RED
@@ -158,9 +168,9 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
     cur[p] = -1;
     fv[p] = (h0 + p < prm.h) ? frag_load<T, X>(feat + ((int64_t)bn * hw + (h0 + p) * prm.w + ww) * C, sc) : frag_zero<X>();
   }
-  const int4* rank_col = s_rank4 + warp + grp * kScW;       // this lane group's first bin
-  const float4* depth_col = s_depth4 + warp + grp * kScW;
-  const int* lead_col = s_lead + warp + grp * kScW;
+  const int4* rank_col = s_rank4 + wcol + grp * WB;       // this lane group's first bin
+  const float4* depth_col = s_depth4 + wcol + grp * WB;
+  const int* lead_col = s_lead + wcol + grp * WB;
 
   // point (row p, rank rp, depth dp): join the accumulator holding voxel rp, else evict row p's accumulator
 #define BEVPOOL_SC_PUT(p, rp, dp)                                                        \
@@ -180,13 +190,13 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
   // every shared-memory access has an immediate offset. (Routing the summaries through a warp reduction to get
   // them into uniform registers removes the BSSY/BSYNC bookkeeping but CREDUX costs as much: measured equal.)
   int cur0 = -1;
-  for (int d0 = 0; d0 < d_pad; d0 += 4 * G) {
+  for (int d0 = d_lo; d0 < d_hi; d0 += 4 * G) {
     int lead[4];
     float4 dp[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      lead[u] = lead_col[(d0 + G * u) * kScW];     // broadcast LDS (per lane group)
-      dp[u] = depth_col[(d0 + G * u) * kScW];      // broadcast LDS.128
+      lead[u] = lead_col[(d0 + G * u) * WB];     // broadcast LDS (per lane group)
+      dp[u] = depth_col[(d0 + G * u) * WB];      // broadcast LDS.128
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -207,7 +217,7 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
         continue;
       }
       cur[0] = cur0;
-      const int4 r = rank_col[(d0 + G * u) * kScW];
+      const int4 r = rank_col[(d0 + G * u) * WB];
       BEVPOOL_SC_PUT(0, r.x, dp[u].x)
       BEVPOOL_SC_PUT(1, r.y, dp[u].y)
       BEVPOOL_SC_PUT(2, r.z, dp[u].z)
@@ -267,17 +277,38 @@ acc_convert_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n
     Vec4<T>::store(dst, 4 * i, Vec4<float>::load_stream(src, 4 * i));
 }
 
-template <typename T, int CH4>
-static void scatter_launch(const void* depth, const void* feat, const float* frustum, const float* rots, const float* trans,
-                           const ScatterParams& prm, int32_t* point_rank, float* acc, unsigned blocks, size_t smem,
-                           cudaStream_t st) {
+template <typename T, int CH4, int HALVES>
+static void scatter_launch_h(const void* depth, const void* feat, const float* frustum, const float* rots, const float* trans,
+                             const ScatterParams& prm, int32_t* point_rank, float* acc, unsigned blocks, size_t smem,
+                             cudaStream_t st) {
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
-    cudaFuncSetAttribute(view_fwd_scatter_kernel<T, CH4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(view_fwd_scatter_kernel<T, CH4, HALVES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = smem;
   }
-  launch_pdl(view_fwd_scatter_kernel<T, CH4>, dim3(blocks), dim3(kScThreads), smem, st, (const T*)depth, (const T*)feat, frustum,
-             rots, trans, prm, point_rank, acc);
+  launch_pdl(view_fwd_scatter_kernel<T, CH4, HALVES>, dim3(blocks), dim3(kScThreads), smem, st, (const T*)depth, (const T*)feat,
+             frustum, rots, trans, prm, point_rank, acc);
+}
+
+// Few waves of 8-column CTAs: use 4-column CTAs with the depth range split over two warps (shorter tail).
+template <typename T, int CH4>
+static int scatter_launch(const void* depth, const void* feat, const float* frustum, const float* rots, const float* trans,
+                          ScatterParams prm, int32_t* point_rank, float* acc, cudaStream_t st) {
+  prm.blocks_h = (prm.h + kScH - 1) / kScH;
+  const int64_t blocks8 = (int64_t)prm.bn * ((prm.w + kScW - 1) / kScW) * prm.blocks_h;
+  const char* env = getenv("BEVPOOL_FWD_HALVES");
+  const bool split = env ? atoi(env) == 2 : blocks8 < (int64_t)kNumSMs * 3 * 4;   // under 4 waves (measured: no gain beyond)
+  const int wb = split ? kScW / 2 : kScW;
+  prm.blocks_w = (prm.w + wb - 1) / wb;
+  const int64_t blocks = (int64_t)prm.bn * prm.blocks_w * prm.blocks_h;
+  if (blocks > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
+  const size_t smem = (size_t)((prm.d + 31) & ~31) * wb * (sizeof(int4) + sizeof(float4) + sizeof(int));
+  if (smem > 200 * 1024) return BEVPOOL_ERR_BAD_ARG;
+  if (blocks == 0) return 0;
+  if (split) scatter_launch_h<T, CH4, 2>(depth, feat, frustum, rots, trans, prm, point_rank, acc, (unsigned)blocks, smem, st);
+  else scatter_launch_h<T, CH4, 1>(depth, feat, frustum, rots, trans, prm, point_rank, acc, (unsigned)blocks, smem, st);
+  count_launch();
+  return 0;
 }
 
 template <typename T>
@@ -288,22 +319,15 @@ static int view_forward_t(const void* depth, const void* feat, const float* frus
   const bool direct = layout == BEVPOOL_LAYOUT_BZYXC && sizeof(T) == 4;   // REDs land in the caller's tensor
   float* acc = direct ? (float*)out : (float*)scratch;
   cudaMemsetAsync(acc, 0, (size_t)n_vox * prm.c * sizeof(float), st);
-  prm.blocks_w = (prm.w + kScW - 1) / kScW;
-  prm.blocks_h = (prm.h + kScH - 1) / kScH;
-  const int64_t blocks = (int64_t)prm.bn * prm.blocks_w * prm.blocks_h;
-  if (blocks > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
-  const size_t smem = (size_t)((prm.d + 15) & ~15) * kScW * (sizeof(int4) + sizeof(float4) + sizeof(int));
-  if (smem > 200 * 1024) return BEVPOOL_ERR_BAD_ARG;
-  if (blocks > 0) {
-    switch (prm.c) {
-      case 32: scatter_launch<T, 8>(depth, feat, frustum, rots, trans, prm, point_rank, acc, (unsigned)blocks, smem, st); break;
-      case 64: scatter_launch<T, 16>(depth, feat, frustum, rots, trans, prm, point_rank, acc, (unsigned)blocks, smem, st); break;
-      case 80: scatter_launch<T, 20>(depth, feat, frustum, rots, trans, prm, point_rank, acc, (unsigned)blocks, smem, st); break;
-      case 128: scatter_launch<T, 32>(depth, feat, frustum, rots, trans, prm, point_rank, acc, (unsigned)blocks, smem, st); break;
-      default: scatter_launch<T, 0>(depth, feat, frustum, rots, trans, prm, point_rank, acc, (unsigned)blocks, smem, st); break;
-    }
-    count_launch();
+  int rc;
+  switch (prm.c) {
+    case 32: rc = scatter_launch<T, 8>(depth, feat, frustum, rots, trans, prm, point_rank, acc, st); break;
+    case 64: rc = scatter_launch<T, 16>(depth, feat, frustum, rots, trans, prm, point_rank, acc, st); break;
+    case 80: rc = scatter_launch<T, 20>(depth, feat, frustum, rots, trans, prm, point_rank, acc, st); break;
+    case 128: rc = scatter_launch<T, 32>(depth, feat, frustum, rots, trans, prm, point_rank, acc, st); break;
+    default: rc = scatter_launch<T, 0>(depth, feat, frustum, rots, trans, prm, point_rank, acc, st); break;
   }
+  if (rc) return rc;
   if (direct) return launch_status();
   if (layout == BEVPOOL_LAYOUT_BZYXC) {
     const int64_t n4 = n_vox * prm.c / 4;
