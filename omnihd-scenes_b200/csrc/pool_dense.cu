@@ -982,18 +982,32 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
     const int4* rank_col = s_rank4 + warp;
     const float4* depth_col = s_depth4 + warp;
     const int* lead_col = s_lead + warp;
+    // Software pipeline over passes of 4 bins: the out_grad rows of pass t + 1 are requested before pass t is
+    // consumed, so the L2 round trip of the gather overlaps this warp's own arithmetic (with 4 warps per scheduler
+    // the other warps alone do not cover it).
+    int code_n[NU];
+    Frag<X> g_n[NU];
+    auto request = [&](int dbase) {
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        code_n[u] = dbase < d_pad ? lead_col[(dbase + G * u + grp) * kPixW] : -1;   // broadcast LDS (per lane group)
+        g_n[u] = frag_zero<X>();
+        if (code_n[u] != -1) g_n[u] = frag_load<T, X>(og + (int64_t)(code_n[u] >= 0 ? code_n[u] : -2 - code_n[u]) * C, sc);
+      }
+    };
+    request(0);
     for (int d0 = 0; d0 < prm.d; d0 += kJointBins) {
 #pragma unroll
       for (int k0 = 0; k0 < kJointBins; k0 += 4) {
-        // NU bins per lane group at a time (bins k0 + G*u + grp): lead rows requested first, then consumed
+        // NU bins per lane group at a time (bins k0 + G*u + grp)
         int code[NU];
         Frag<X> g[NU];
 #pragma unroll
         for (int u = 0; u < NU; ++u) {
-          code[u] = lead_col[(d0 + k0 + G * u + grp) * kPixW];   // broadcast LDS (per lane group)
-          g[u] = frag_zero<X>();
-          if (code[u] != -1) g[u] = frag_load<T, X>(og + (int64_t)(code[u] >= 0 ? code[u] : -2 - code[u]) * C, sc);
+          code[u] = code_n[u];
+          g[u] = g_n[u];
         }
+        request(d0 + k0 + 4);
         int cmax = code[0], cmin = code[0];
 #pragma unroll
         for (int u = 1; u < NU; ++u) {
