@@ -1049,23 +1049,24 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
             }
           } else {
             // mixed column: rows of one voxel are adjacent (height is monotonic along the column), so a row is
-            // loaded once per RUN of equal ranks; the largest rank's row is already in g[u]
+            // loaded once per RUN of equal ranks (the largest rank's row is already in g[u]); all loads of the bin
+            // are issued before the first use
             const int lead = -2 - code[u];
             const int4 r4 = rank_col[dd * kPixW];
             const int rr[kPixH] = {r4.x, r4.y, r4.z, r4.w};
-            Frag<X> gp = g[u];
-            int rp = lead;
+            Frag<X> gp[kPixH];
+#pragma unroll
+            for (int p = 0; p < kPixH; ++p) {
+              if (rr[p] < 0 || rr[p] == lead) gp[p] = g[u];
+              else if (p > 0 && rr[p] == rr[p - 1]) gp[p] = gp[p - 1];
+              else gp[p] = frag_load<T, X>(og + (int64_t)rr[p] * C, sc);
+            }
 #pragma unroll
             for (int p = 0; p < kPixH; ++p) {
               dt[p] = 0.f;
               if (rr[p] >= 0) {
-                if (rr[p] != rp) {
-                  rp = rr[p];
-                  if (rp == lead) gp = g[u];
-                  else gp = frag_load<T, X>(og + (int64_t)rp * C, sc);
-                }
-                fg[p] = frag_fma<X>(gp, dw[p], fg[p]);
-                dt[p] = frag_dot<X>(gp, fv[p]);
+                fg[p] = frag_fma<X>(gp[p], dw[p], fg[p]);
+                dt[p] = frag_dot<X>(gp[p], fv[p]);
               }
             }
           }
