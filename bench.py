@@ -280,6 +280,21 @@ def run_native_arm(args):
         variants["channels_last_3d_grid"] = {"value": world * B * args.steps / (ms_v * 1e-3), "unit": UNIT,
                                              "ms_per_step": ms_v / args.steps}
 
+        # the reference's own call sequence (get_geometry -> voxel_pooling_prepare_v2 -> bev_pool_v2, as
+        # LiftSplatShoot.get_voxels does): coor is materialised, prepare returns exact-length sorted rank tensors
+        # (one 8-byte device->host read per step), so it runs eagerly, not as a graph
+        def api_step(i):
+            s = sets[i % N_BUFFER_SETS]
+            s["depth"].grad = None
+            s["feat"].grad = None
+            bev = view.voxel_pooling_v2(view.get_geometry(s["rots"], s["trans"]), s["depth"], s["feat"])
+            bev.backward(s["gout"])
+        api_steps = max(3, min(args.steps, 50))
+        ms_a = timed(api_step, api_steps, 3)
+        variants["reference_api_sequence"] = {"value": world * B * api_steps / (ms_a * 1e-3), "unit": UNIT,
+                                              "ms_per_step": ms_a / api_steps,
+                                              "note": "get_geometry + voxel_pooling_prepare_v2 + bev_pool_v2 + backward, eager"}
+
     # ---- (2) e2e: pinned host buffers -> H2D -> graph -> D2H, every step, same public API
     out_host = [dict(bev=torch.empty((B, C, Z, Y, X), dtype=dt_t).pin_memory(),
                      dg=torch.empty((B, N, D, H, W), dtype=dt_t).pin_memory(),
