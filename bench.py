@@ -146,6 +146,25 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this rank's host threads (and so its first-touched pinned buffers) to the CPUs next to its GPU, as any
+    multi-GPU launcher does: with 8 ranks the e2e copies otherwise cross the socket interconnect. Best effort."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        cpus = set()
+        for part in open(f"/sys/bus/pci/devices/{dev}/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"pci": dev, "cpus": len(cpus)}
+    except (OSError, ValueError, AttributeError):
+        pass
+    return None
+
+
 def run_native_arm(args):
     import torch
     import torch.distributed as dist
@@ -160,6 +179,7 @@ def run_native_arm(args):
         raise SystemExit("bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 and not args.no_numa_bind else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -491,7 +511,7 @@ def run_native_arm(args):
                    "forward_path": "deterministic(sorted)" if view.deterministic else "scatter(sort-free, fp32 REDs)",
                    "frame_groups": groups,
                    "l2": f"inputs rotated over {N_BUFFER_SETS} buffer sets (> 126 MB L2 in total), no explicit flush",
-                   "parallelism": f"frame-sharded x{world}, no collective on the path"},
+                   "parallelism": f"frame-sharded x{world}, no collective on the path", "numa_bind": numa},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
         "gpu_launches": launches_per_step * args.steps,
@@ -524,6 +544,7 @@ def main():
     ap.add_argument("--config", default=WORKLOAD)
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU (default: the config's batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin ranks to the CPUs local to their GPU")
     ap.add_argument("--no-variants", action="store_true", help="skip the channels_last_3d variant measurement")
     ap.add_argument("--time-sorted-path", action="store_true",
                     help="also time the kernels of the sorted (deterministic) forward for comparison")
