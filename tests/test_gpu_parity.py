@@ -666,10 +666,11 @@ def test_pillar_scatter_vs_oracle(pkg, orc, B, C, ny, nx, P, dt):
         assert float(f2.grad[0].abs().max()) == 0.0 and float(f2.grad[-1].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("C", [4, 32, 64, 128])
+@pytest.mark.parametrize("C", [4, 32, 64, 128, 132])
 def test_fused_path_channel_counts_z1(pkg, orc, C):
     """Z = 1 grid with the channel counts that select the other lane mappings of the fused kernels (C <= 32: four lane
-    groups, C <= 64: two, C = 128: one full-width group, C = 4: the generic block backward), fwd + bwd vs the oracle."""
+    groups, C <= 64: two, C = 128: one full-width group, C = 4: the generic block backward, C = 132 > 128: the sorted
+    forward with the tile kernel and the channel-chunked block backward), fwd + bwd vs the oracle."""
     import dataclasses
     cfg = dataclasses.replace(pkg.synthetic.CONFIGS["bevdet_r50_b8"], channels=C)
     B = 2
