@@ -906,9 +906,12 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
 
   const int blk = blockIdx.x;
   const int per_img = prm.blocks_w * prm.blocks_h;
-  const int bn = blk / per_img;
-  const int brem = blk - bn * per_img;
-  const int bh = brem / prm.blocks_w, bw = brem - bh * prm.blocks_w;
+  // block order: image rows from the bottom up, all images of a row band together. Bands differ a lot in kept
+  // points (upper rows leave the z-range early); with the lightest band last the tail of the last wave is short.
+  const int per_band = prm.bn * prm.blocks_w;
+  const int bh = prm.blocks_h - 1 - blk / per_band;
+  const int brem = blk % per_band;
+  const int bn = brem / prm.blocks_w, bw = brem - bn * prm.blocks_w;
   const int h0 = bh * kPixH, w0 = bw * kPixW;
   const int hw = prm.h * prm.w;
   const int64_t img_base = (int64_t)bn * prm.d * hw;
