@@ -152,3 +152,20 @@ def test_frame_sharding_and_all_gather_gloo_world2():
     for p in procs:
         p.join(60)
     assert res == [(0, True, (2, 3, 2, 5, 5)), (1, True, (2, 3, 2, 5, 5))]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` runs without a GPU (it times the CPU port of the reference path) and prints one
+    JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "bev_pool_fwd_bwd_frames_per_s" and line["unit"] == "frames/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1
+    assert line["config"]["workload"] == "bevdet_r50_b8"
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["e2e"]["value"] == line["value"]
