@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #include "../../include/bevpool_b200.h"
@@ -237,13 +238,22 @@ __device__ __forceinline__ void cam_point(const float* __restrict__ frustum, con
   z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cam[6], px), __fmul_rn(cam[7], py)), __fmul_rn(cam[8], pz)), cam[11]);
 }
 
-__device__ __forceinline__ bool voxel_index(float c, float lo, float dx, int n, int& v) {
-  const float q = __fdiv_rn(__fsub_rn(c, lo), dx);
+// inv > 0: dx is a power of two and inv = 1/dx exactly, so the IEEE divide is a multiply (bit-identical: both are the
+// correctly rounded value of the same real number); inv == 0: true divide.
+__device__ __forceinline__ bool voxel_index(float c, float lo, float dx, float inv, int n, int& v) {
+  const float t = __fsub_rn(c, lo);
+  const float q = inv > 0.f ? __fmul_rn(t, inv) : __fdiv_rn(t, dx);
   // .long() truncates toward zero, so (-1, 0) lands in voxel 0 and is KEPT; trunc(q) in [0, n) <=> -1 < q < n
   // (n < 2^24 is exact in fp32). NaN / inf fail both comparisons (the CPU's INT64_MIN is dropped too).
   if (!(q > -1.0f && q < (float)n)) return false;
   v = (int)q;
   return true;
+}
+
+// 1/dx if dx is a positive power of two (then exact), else 0
+inline float exact_reciprocal_or_zero(float dx) {
+  int e = 0;
+  return (dx > 0.f && frexpf(dx, &e) == 0.5f) ? 1.0f / dx : 0.f;
 }
 
 }  // namespace bevpool

@@ -34,7 +34,7 @@ struct ScatterParams {
   int bn, n_cams;
   int blocks_w, blocks_h;
   int nx, ny, nz;
-  float lo[3], dx[3];
+  float lo[3], dx[3], inv[3];   // inv: see voxel_index
   int from_geometry;   // 1: compute ranks from frustum/rots/trans and write point_rank; 0: read point_rank
 };
 
@@ -126,8 +126,9 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
             float x, y, z;
             cam_point(frustum, s_cam, o, x, y, z);
             int vx, vy, vz;
-            const bool ok = voxel_index(x, prm.lo[0], prm.dx[0], prm.nx, vx) & voxel_index(y, prm.lo[1], prm.dx[1], prm.ny, vy) &
-                            voxel_index(z, prm.lo[2], prm.dx[2], prm.nz, vz);
+            const bool ok = voxel_index(x, prm.lo[0], prm.dx[0], prm.inv[0], prm.nx, vx) &
+                            voxel_index(y, prm.lo[1], prm.dx[1], prm.inv[1], prm.ny, vy) &
+                            voxel_index(z, prm.lo[2], prm.dx[2], prm.inv[2], prm.nz, vz);
             if (ok) r[k] = (int)(frame_base + ((int64_t)vz * prm.ny + vy) * prm.nx + vx);
             point_rank[img_base + o] = r[k];
           } else {
@@ -400,6 +401,7 @@ extern "C" int bevpool_view_forward(const void* depth, const void* feat, const f
   for (int a = 0; a < 3; ++a) {
     prm.lo[a] = g->lo[a];
     prm.dx[a] = g->dx[a];
+    prm.inv[a] = exact_reciprocal_or_zero(g->dx[a]);
   }
   prm.from_geometry = from_geometry ? 1 : 0;
   prm.blocks_w = prm.blocks_h = 0;

@@ -132,7 +132,7 @@ struct GridDev {
   int n_cams;          // N
   int bn;              // B*N
   int nx, ny, nz;
-  float lo[3], dx[3];
+  float lo[3], dx[3], inv[3];   // inv: see voxel_index
 };
 
 // One CTA = one sort tile of the (uncompacted) point list: rank of every point, the tile's pass-0
@@ -174,8 +174,8 @@ point_rank_kernel(const float* __restrict__ coor, const float* __restrict__ frus
         cam_point(frustum, s_cam + cam * 12, idx - (int64_t)cam * g.dhw, x, y, z);
       }
       int vx, vy, vz;
-      const bool ok = voxel_index(x, g.lo[0], g.dx[0], g.nx, vx) & voxel_index(y, g.lo[1], g.dx[1], g.ny, vy) &
-                      voxel_index(z, g.lo[2], g.dx[2], g.nz, vz);
+      const bool ok = voxel_index(x, g.lo[0], g.dx[0], g.inv[0], g.nx, vx) & voxel_index(y, g.lo[1], g.dx[1], g.inv[1], g.ny, vy) &
+                      voxel_index(z, g.lo[2], g.dx[2], g.inv[2], g.nz, vz);
       int rank = -1;
       if (ok) {
         rank = (int)((int64_t)(cam / g.n_cams) * vpf + ((int64_t)vz * g.ny + vy) * g.nx + vx);
@@ -611,6 +611,7 @@ extern "C" int bevpool_prepare_v2(const float* coor, const float* frustum, const
   for (int a = 0; a < 3; ++a) {
     gd.lo[a] = g->lo[a];
     gd.dx[a] = g->dx[a];
+    gd.inv[a] = exact_reciprocal_or_zero(g->dx[a]);
   }
   if (coor) {
     point_rank_kernel<true><<<(unsigned)plan.n_tiles, kSortThreads, 0, st>>>(coor, frustum, rots, trans, gd, plan,
