@@ -22,6 +22,8 @@
  *   bevpool_v2_backward_dense     bev_pool.py:47-57,67-70 (argsort, zeros, kernel) in one pass
  *
  *   bevpool_lift_forward / _backward  bevfusion/detectors/cam_stream_lss_bevpoolv2.py:134-141 (+ :282)
+ *   bevpool_channel_avg_max_*, bevpool_gate_concat_*  rcfusion/detectors/BEVCross_modal_attention.py:31-43
+ *   bevpool_pillar_scatter_*          rcfusion/detectors/rcfusion_faster_rcnn.py:100 (mmdet3d PointPillarsScatter)
  *   bevpool_v1_forward / _backward ops/bev_pool/src/bev_pool.cpp:27-94, src/bev_pool_cuda.cu:20-84 (v1 op)
  *
  * Argument order note: like the reference's native entry points, interval_lengths
@@ -220,6 +222,24 @@ int bevpool_pillar_scatter_forward(const void* voxel_features, const int32_t* co
                                    void* stream);
 int bevpool_pillar_scatter_backward(const void* canvas_grad, const int32_t* coors, void* voxel_grad, int n_pillars,
                                     int c, int b, int ny, int nx, int dtype, void* stream);
+
+/* ------------------------------------------------------------------ cross-modal fusion glue
+ * The bandwidth-bound pieces of Cross_Modal_Fusion.forward (rcfusion/detectors/BEVCross_modal_attention.py:31-43)
+ * around its convolutions, NCHW contiguous tensors:
+ *   channel_avg_max: out [B,2,H,W] = cat(mean over C, max over C) of x [B,C,H,W] (:32-34, :36-38); argmax [B,H,W]
+ *                    int32 is written for the backward (first maximum wins, as torch.max).
+ *   gate_concat:     out [N,Ca+Cb,H,W] = cat(a * att_for_a, b * att_for_b) with att_* [N,1,H,W] (:40-42; the
+ *                    reference passes att_for_a = radar_att for a = img_bev and att_for_b = img_att for b = radar_bev).
+ * hw = H*W. The backward entry points write every element of their outputs. */
+int bevpool_channel_avg_max_forward(const void* x, void* out, int32_t* argmax, int b, int c, int64_t hw, int dtype,
+                                    void* stream);
+int bevpool_channel_avg_max_backward(const void* out_grad, const int32_t* argmax, void* x_grad, int b, int c,
+                                     int64_t hw, int dtype, void* stream);
+int bevpool_gate_concat_forward(const void* a, const void* b, const void* att_for_a, const void* att_for_b, void* out,
+                                int n, int ca, int cb, int64_t hw, int dtype, void* stream);
+int bevpool_gate_concat_backward(const void* out_grad, const void* a, const void* b, const void* att_for_a,
+                                 const void* att_for_b, void* a_grad, void* b_grad, void* att_for_a_grad,
+                                 void* att_for_b_grad, int n, int ca, int cb, int64_t hw, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ library `csrc/libbevpool_b200.so` (include/bevpool_b200.h). There is no CPU
 fallback: a missing library raises at first use.
 """
 from . import build, _lib, synthetic            # noqa: F401
-from . import view_transform, bev_pool, bev_pool_v1, lift, pillar_scatter, plugin, sharding   # noqa: F401
+from . import view_transform, bev_pool, bev_pool_v1, lift, pillar_scatter, cross_modal, plugin, sharding   # noqa: F401
 from .lift import get_depth_feat, get_depth_dist   # noqa: F401
 from .bev_pool import bev_pool_v2, TRTBEVPoolv2, QuickCumsumCuda   # noqa: F401
 from .view_transform import (gen_dx_bx, create_frustum, get_geometry,       # noqa: F401

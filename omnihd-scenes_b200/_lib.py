@@ -50,6 +50,10 @@ SIGNATURES = {
                                      c_int, c_int, c_void_p, ctypes.c_size_t, c_void_p]),
     "bevpool_pillar_scatter_forward": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     "bevpool_pillar_scatter_backward": (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
+    "bevpool_channel_avg_max_forward": (c_int, [c_void_p] * 3 + [c_int, c_int, c_i64, c_int, c_void_p]),
+    "bevpool_channel_avg_max_backward": (c_int, [c_void_p] * 3 + [c_int, c_int, c_i64, c_int, c_void_p]),
+    "bevpool_gate_concat_forward": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_i64, c_int, c_void_p]),
+    "bevpool_gate_concat_backward": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_i64, c_int, c_void_p]),
     "bevpool_lift_forward": (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
     "bevpool_lift_backward": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     "bevpool_grid_transpose": (c_int, [c_void_p, c_void_p, c_int, c_int, c_i64, c_int, c_int, c_void_p]),

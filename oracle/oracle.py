@@ -207,6 +207,37 @@ def lift_head_backward(depth, depth_grad, feat_grad):
     return np.concatenate([dx.astype(np.float32), np.asarray(feat_grad, dtype=np.float32)], axis=1)
 
 
+# --------------------------------------------------------------------------- cross-modal fusion glue
+def channel_avg_max(x):
+    """BEVCross_modal_attention.py:32-34 / :36-38: cat([mean over C, max over C], 1), float64 mean rounded once."""
+    x = np.asarray(x, dtype=np.float32)
+    return np.stack([x.astype(np.float64).mean(axis=1).astype(np.float32), x.max(axis=1)], axis=1)
+
+
+def channel_avg_max_backward(x, g):
+    """mean: g/C to every channel; max: g to the FIRST maximal channel (torch.max's gradient)."""
+    x = np.asarray(x, dtype=np.float32)
+    B, C, H, W = x.shape
+    dx = np.repeat((g[:, 0:1].astype(np.float64) / C), C, axis=1)
+    am = x.argmax(axis=1)
+    bi, hi, wi = np.meshgrid(np.arange(B), np.arange(H), np.arange(W), indexing="ij")
+    dx[bi, am, hi, wi] += g[:, 1].astype(np.float64)
+    return dx.astype(np.float32)
+
+
+def gate_concat(a, b, att_for_a, att_for_b):
+    """:40-42: cat([a * att_for_a, b * att_for_b], 1)."""
+    return np.concatenate([a * att_for_a, b * att_for_b], axis=1).astype(np.float32)
+
+
+def gate_concat_backward(g, a, b, att_for_a, att_for_b):
+    ca = a.shape[1]
+    g64 = g.astype(np.float64)
+    return ((g[:, :ca] * att_for_a).astype(np.float32), (g[:, ca:] * att_for_b).astype(np.float32),
+            (g64[:, :ca] * a).sum(axis=1, keepdims=True).astype(np.float32),
+            (g64[:, ca:] * b).sum(axis=1, keepdims=True).astype(np.float32))
+
+
 # --------------------------------------------------------------------------- pillar scatter
 def pillar_scatter(voxel_features, coors, batch_size, ny, nx):
     """mmdet3d v0.17.1 PointPillarsScatter.forward_batch (the reference's pts_middle_encoder,

@@ -20,6 +20,7 @@ the reference outputs of one case. The reference's only known-answer test
 (ops/bev_pool_v2/bev_pool.py:145-176) is transcribed as kat_bev_pool_v2.npz.
 """
 import importlib
+import importlib.util
 import os
 import sys
 import types
@@ -216,6 +217,30 @@ def main():
                         feat=fl.detach().numpy(), depth_grad=gd.numpy(), feat_grad=gf.numpy(),
                         x_grad=(gx_d + xl.grad).numpy(), dims=np.array([Dl, Cl]))
     print("lift golden", tuple(dl.shape), tuple(fl.shape))
+
+    # cross-modal fusion glue: the reference's Cross_Modal_Fusion.forward (BEVCross_modal_attention.py:31-43) with
+    # mmcv's ConvModule (the final 3x3 reduction conv) replaced by identity, so the output is the gated concat;
+    # gradients from autograd
+    class _IdentityConvModule(torch.nn.Identity):
+        def __init__(self, *a, **k):
+            super().__init__()
+    sys.modules["mmcv.cnn"].ConvModule = _IdentityConvModule
+    sys.modules["mmcv.cnn"].xavier_init = lambda *a, **k: None
+    spec = importlib.util.spec_from_file_location(
+        "ref_cross_modal", os.path.join(REF, "projects/mmdet3d_plugin/rcfusion/detectors/BEVCross_modal_attention.py"))
+    cm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cm)
+    torch.manual_seed(13)
+    fus = cm.Cross_Modal_Fusion(kernel_size=3)
+    img = torch.randn(2, 6, 5, 9, requires_grad=True)
+    rad = torch.randn(2, 10, 5, 9, requires_grad=True)
+    outf = fus(img, rad)
+    gof = torch.randn_like(outf)
+    outf.backward(gof)
+    np.savez_compressed(os.path.join(HERE, "cross_modal.npz"), img=img.detach().numpy(), radar=rad.detach().numpy(),
+                        w_img=fus.att_img[0].weight.detach().numpy(), w_radar=fus.att_radar[0].weight.detach().numpy(),
+                        out=outf.detach().numpy(), out_grad=gof.numpy(), img_grad=img.grad.numpy(), radar_grad=rad.grad.numpy())
+    print("cross-modal golden", tuple(outf.shape))
 
     # the reference's own KAT, transcribed (ops/bev_pool_v2/bev_pool.py:145-176)
     np.savez(os.path.join(HERE, "kat_bev_pool_v2.npz"),

@@ -714,3 +714,53 @@ def test_fused_path_ragged_feature_map(pkg, orc, zb, C):
         bev.backward(gout.to(DEV))
         assert rel_to_max(d.grad.cpu().numpy(), gd) <= TOL
         assert rel_to_max(f.grad.permute(0, 1, 3, 4, 2).cpu().numpy(), gf) <= TOL
+
+
+# ------------------------------------------------------------------------------------------ cross-modal fusion (§8(f) rank 4)
+def test_cross_modal_fusion_vs_reference_golden(pkg):
+    """Cross_Modal_Fusion mirror with the reference's attention-conv weights: its `fuse` (everything before the final
+    3x3 reduction conv) must reproduce the reference module's output and input gradients."""
+    g = load("cross_modal")
+    m = pkg.cross_modal.Cross_Modal_Fusion(kernel_size=3, img_channels=6, radar_channels=10, out_channels=4).to(DEV)
+    assert sorted(k for k, _ in m.named_parameters()) == ['att_img.0.weight', 'att_radar.0.weight', 'reduce_mixBEV.conv.bias',
+                                                           'reduce_mixBEV.conv.weight']
+    with torch.no_grad():
+        m.att_img[0].weight.copy_(cu(g["w_img"]))
+        m.att_radar[0].weight.copy_(cu(g["w_radar"]))
+    img, rad = cu(g["img"]).requires_grad_(), cu(g["radar"]).requires_grad_()
+    out = m.fuse(img, rad)
+    assert rel_to_max(out.detach().cpu().numpy(), g["out"]) <= TOL
+    out.backward(cu(g["out_grad"]))
+    assert rel_to_max(img.grad.cpu().numpy(), g["img_grad"]) <= TOL
+    assert rel_to_max(rad.grad.cpu().numpy(), g["radar_grad"]) <= TOL
+    assert m(img.detach(), rad.detach()).shape == (2, 4, 5, 9)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_cross_modal_glue_kernels_vs_oracle(pkg, orc, dt):
+    """channel_avg_max / gate_concat at the RCFusion size (256 + 384 channels, 160 x 240 BEV), ties in the max
+    (first index wins), fwd + bwd vs the oracle."""
+    rng = np.random.default_rng(21)
+    N, Ca, Cb, H, W = 2, 256, 384, 160, 240
+    tol = TOL if dt == torch.float32 else 2 ** -7
+    x = rng.standard_normal((N, Ca, H, W)).astype(np.float32)
+    x[:, 7] = x[:, 3] = x.max(axis=1) + 1.0                                   # two maximal channels: 3 must win
+    xt = cu(x).to(dt).requires_grad_()
+    xin = xt.detach().float().cpu().numpy()
+    out = pkg.cross_modal.channel_avg_max(xt)
+    ref = orc.channel_avg_max(xin)
+    assert rel_to_max(out.detach().float().cpu().numpy(), ref) <= tol
+    gm = rng.standard_normal(ref.shape).astype(np.float32)
+    gmt = cu(gm).to(dt)
+    out.backward(gmt)
+    assert rel_to_max(xt.grad.float().cpu().numpy(), orc.channel_avg_max_backward(xin, gmt.float().cpu().numpy())) <= tol
+    b = rng.standard_normal((N, Cb, H, W)).astype(np.float32)
+    wa, wb = rng.random((N, 1, H, W), dtype=np.float32), rng.random((N, 1, H, W), dtype=np.float32)
+    ts = [cu(v).to(dt).requires_grad_() for v in (x, b, wa, wb)]
+    ins = [t.detach().float().cpu().numpy() for t in ts]
+    cat = pkg.cross_modal.gate_concat(*ts)
+    assert rel_to_max(cat.detach().float().cpu().numpy(), orc.gate_concat(*ins)) <= tol
+    gc = cu(rng.standard_normal((N, Ca + Cb, H, W)).astype(np.float32)).to(dt)
+    cat.backward(gc)
+    for t, want in zip(ts, orc.gate_concat_backward(gc.float().cpu().numpy(), *ins)):
+        assert rel_to_max(t.grad.float().cpu().numpy(), want) <= (tol if dt == torch.float32 else 2 ** -6)

@@ -186,3 +186,29 @@ def test_pillar_scatter_oracle_vs_torch_index_assignment(orc):
     assert np.array_equal(got, want.view(B, C, ny, nx).numpy())
     g = rng.standard_normal(got.shape).astype(np.float32)
     assert np.array_equal(orc.pillar_scatter_backward(g, coors), g[coors[:, 0], :, coors[:, 2], coors[:, 3]])
+
+
+def test_cross_modal_glue_matches_reference_module(orc):
+    """§8(f) rank 4: the reference's Cross_Modal_Fusion.forward run from the reference file itself (final ConvModule
+    replaced by identity -> the gated concat) with its autograd gradients. The oracle's glue functions, chained with
+    torch's conv + sigmoid for the two 3x3 attention convs, must reproduce it."""
+    import torch
+    import torch.nn.functional as F
+    g = np.load(os.path.join(GOLDEN, "cross_modal.npz"))
+    img, rad = g["img"], g["radar"]
+    att = lambda x, w: torch.sigmoid(F.conv2d(torch.from_numpy(orc.channel_avg_max(x)), torch.from_numpy(w), padding=1)).numpy()
+    img_att, radar_att = att(img, g["w_img"]), att(rad, g["w_radar"])
+    out = orc.gate_concat(img, rad, radar_att, img_att)
+    assert rel_to_max(out, g["out"]) <= 1e-6
+    # gradients: chain the oracle's backward pieces through torch's conv/sigmoid backward
+    ti, tr = torch.from_numpy(img).requires_grad_(), torch.from_numpy(rad).requires_grad_()
+    am_i = torch.from_numpy(orc.channel_avg_max(img)).requires_grad_()
+    am_r = torch.from_numpy(orc.channel_avg_max(rad)).requires_grad_()
+    ia = torch.sigmoid(F.conv2d(am_i, torch.from_numpy(g["w_img"]), padding=1))
+    ra = torch.sigmoid(F.conv2d(am_r, torch.from_numpy(g["w_radar"]), padding=1))
+    da, db, dra, dia = orc.gate_concat_backward(g["out_grad"], img, rad, ra.detach().numpy(), ia.detach().numpy())
+    ia.backward(torch.from_numpy(dia))
+    ra.backward(torch.from_numpy(dra))
+    gi = da + orc.channel_avg_max_backward(img, am_i.grad.numpy())
+    gr = db + orc.channel_avg_max_backward(rad, am_r.grad.numpy())
+    assert rel_to_max(gi, g["img_grad"]) <= 1e-5 and rel_to_max(gr, g["radar_grad"]) <= 1e-5
