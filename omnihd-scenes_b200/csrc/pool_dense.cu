@@ -802,32 +802,39 @@ pool_bwd_block_half_kernel(const T* __restrict__ og, const T* __restrict__ depth
     const int n_max = max(__shfl_sync(kFullMask, n_kept, 0), __shfl_sync(kFullMask, n_kept, 16));
     const float4 fv = pin ? Vec4<T>::load(feat, pix * prm.c + lane_c) : zero;
     float4 fg = zero;
-    for (int b = 0; b < n_max; b += 8) {
-      float4 g[8];
-      float dv[8], pr[8];
+    // batches of 4 points, software-pipelined: the out_grad rows of the next batch are requested before the current
+    // one is consumed (the loop is bound by the latency of these gathers, not by their bandwidth)
+    float4 g_n[4];
+    float d_n[4];
+    auto request = [&](int b0) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        g[u] = zero;
-        dv[u] = 0.f;
-        if (b + u < n_kept) {                     // uniform within the half-warp
-          const int4 e = my_list[b + u];
-          g[u] = Vec4<T>::load(og_lane, (int64_t)e.x * prm.c);
-          dv[u] = __int_as_float(e.y);
+      for (int u = 0; u < 4; ++u) {
+        g_n[u] = zero;
+        d_n[u] = 0.f;
+        if (b0 + u < n_kept) {                     // uniform within the half-warp
+          const int4 e = my_list[b0 + u];
+          g_n[u] = Vec4<T>::load(og_lane, (int64_t)e.x * prm.c);
+          d_n[u] = __int_as_float(e.y);
         }
       }
+    };
+    request(0);
+    for (int b = 0; b < n_max; b += 4) {
+      float4 g[4];
+      float dv[4], pr[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 4; ++u) {
+        g[u] = g_n[u];
+        dv[u] = d_n[u];
+      }
+      request(b + 4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
         fg = fma4(g[u], dv[u], fg);
         pr[u] = act ? dot4_packed(g[u], fv) : 0.f;
       }
-      // reduce-scatter over lane bits 2,1,0, then bit 3 (stays inside the half-warp): lane hl ends up with the
-      // complete dot product of point b + (hl & 7)
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float mine = (lane & 4) ? pr[u + 4] : pr[u];
-        const float send = (lane & 4) ? pr[u] : pr[u + 4];
-        pr[u] = mine + __shfl_xor_sync(kFullMask, send, 4);
-      }
+      // reduce-scatter over lane bits 1,0, then bits 2,3 (inside the half-warp): lane hl ends up with the complete
+      // dot product of point b + (hl & 3)
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const float mine = (lane & 2) ? pr[u + 2] : pr[u];
@@ -839,8 +846,9 @@ pool_bwd_block_half_kernel(const T* __restrict__ og, const T* __restrict__ depth
         const float send = (lane & 1) ? pr[0] : pr[1];
         pr[0] = mine + __shfl_xor_sync(kFullMask, send, 1);
       }
+      pr[0] += __shfl_xor_sync(kFullMask, pr[0], 4);
       pr[0] += __shfl_xor_sync(kFullMask, pr[0], 8);
-      if (hl < 8 && b + hl < n_kept) s_dg[my_list[b + hl].z * kPixBlock + px] = pr[0];
+      if (hl < 4 && b + hl < n_kept) s_dg[my_list[b + hl].z * kPixBlock + px] = pr[0];
     }
     __syncwarp();
     if (prm.feat_grad_nchw) {
