@@ -735,7 +735,7 @@ pool_bwd_block_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
 // Same contract for C <= 64: a row is at most 16 lanes wide, so each HALF-warp takes its own pixel (own compacted
 // list, own out_grad rows, own 16-lane reduce-scatter) and a warp finishes two pixels per pass — twice the lane
 // utilisation of the kernel above on the OmniHD (C = 64) and occupancy (C = 32) shapes.
-template <typename T>
+template <typename T, int CC>     // CC = C when known at compile time (32, 64), 0 = runtime
 __global__ void __launch_bounds__(kBwdThreads)
 pool_bwd_block_half_kernel(const T* __restrict__ og, const T* __restrict__ depth, const T* __restrict__ feat,
                            const int* __restrict__ point_rank, BwdParams prm, T* __restrict__ depth_grad,
@@ -748,7 +748,8 @@ pool_bwd_block_half_kernel(const T* __restrict__ og, const T* __restrict__ depth
   float* s_fg = reinterpret_cast<float*>(s_list + (size_t)kBwdWarps * 2 * prm.d);       // [c][33] (NCHW output only)
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const int half = lane >> 4, hl = lane & 15;
-  const int c4 = prm.c >> 2;   // <= 16
+  const int C = CC ? CC : prm.c;   // the ncu capture showed 40 IMAD + 9 LDC per batch of row-address arithmetic with a runtime C
+  const int c4 = C >> 2;   // <= 16
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 
   const int blk = blockIdx.x;
@@ -798,9 +799,10 @@ pool_bwd_block_half_kernel(const T* __restrict__ og, const T* __restrict__ depth
         my_list[n_kept + __popc(live & ((1u << hl) - 1u))] = make_int4(r, __float_as_int(s_depth[dd * kPixBlock + px]), dd, 0);
       n_kept += __popc(live);
     }
+    if (n_kept == 0 && hl == 0) my_list[0] = make_int4(0, 0, 0, 0);   // so that the clamped re-read below is always valid
     __syncwarp();
     const int n_max = max(__shfl_sync(kFullMask, n_kept, 0), __shfl_sync(kFullMask, n_kept, 16));
-    const float4 fv = pin ? Vec4<T>::load(feat, pix * prm.c + lane_c) : zero;
+    const float4 fv = pin ? Vec4<T>::load(feat, pix * C + lane_c) : zero;
     float4 fg = zero;
     // batches of 4 points, software-pipelined: the out_grad rows of the next batch are requested before the current
     // one is consumed (the loop is bound by the latency of these gathers, not by their bandwidth)
@@ -809,13 +811,11 @@ pool_bwd_block_half_kernel(const T* __restrict__ og, const T* __restrict__ depth
     auto request = [&](int b0) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        g_n[u] = zero;
-        d_n[u] = 0.f;
-        if (b0 + u < n_kept) {                     // uniform within the half-warp
-          const int4 e = my_list[b0 + u];
-          g_n[u] = Vec4<T>::load(og_lane, (int64_t)e.x * prm.c);
-          d_n[u] = __int_as_float(e.y);
-        }
+        // past the end of the list: re-read the pixel's last item with weight 0 (no zero-filled registers, no branch;
+        // its dot product is never stored)
+        const int4 e = my_list[max(min(b0 + u, n_kept - 1), 0)];
+        g_n[u] = Vec4<T>::load(og_lane, (int64_t)e.x * C);
+        d_n[u] = b0 + u < n_kept ? __int_as_float(e.y) : 0.f;
       }
     };
     request(0);
@@ -860,7 +860,7 @@ pool_bwd_block_half_kernel(const T* __restrict__ og, const T* __restrict__ depth
         c[3 * (kPixBlock + 1)] = fg.w;
       }
     } else if (act && pin) {
-      Vec4<T>::store(feat_grad, pix * prm.c + lane_c, fg);
+      Vec4<T>::store(feat_grad, pix * C + lane_c, fg);
     }
   }
   __syncthreads();
@@ -868,8 +868,8 @@ pool_bwd_block_half_kernel(const T* __restrict__ og, const T* __restrict__ depth
   const int hh = h0 + (px >> 3), ww = w0 + (px & 7);
   if (hh < prm.h && ww < prm.w) {
     if (prm.feat_grad_nchw) {
-      const int64_t o0 = (int64_t)bn * prm.c * hw + (int64_t)hh * prm.w + ww;
-      for (int cc = threadIdx.x >> 5; cc < prm.c; cc += kBwdWarps)
+      const int64_t o0 = (int64_t)bn * C * hw + (int64_t)hh * prm.w + ww;
+      for (int cc = threadIdx.x >> 5; cc < C; cc += kBwdWarps)
         Vec4<T>::store1s(feat_grad, o0 + cc * hw, s_fg[cc * (kPixBlock + 1) + px]);
     }
     const int64_t o0 = img_base + (int64_t)hh * prm.w + ww;
@@ -1321,7 +1321,9 @@ static int backward_block_t(const void* og, void* dg, void* fg, const void* dept
   const size_t smem = sizeof(float) * ((size_t)3 * prm.d * kPixBlock + (prm.feat_grad_nchw ? (size_t)cw * (kPixBlock + 1) : 0)) +
                       sizeof(int4) * (size_t)kBwdWarps * prm.d * (half ? 2 : 1);
   if (smem > 200 * 1024) return BEVPOOL_ERR_BAD_ARG;   // D > ~500 depth bins
-  auto kern = half ? pool_bwd_block_half_kernel<T> : pool_bwd_block_kernel<T>;
+  auto kern = !half ? pool_bwd_block_kernel<T>
+                    : (prm.c == 64 ? pool_bwd_block_half_kernel<T, 64>
+                                   : (prm.c == 32 ? pool_bwd_block_half_kernel<T, 32> : pool_bwd_block_half_kernel<T, 0>));
   static size_t attr[2] = {0, 0};
   if (smem > 48 * 1024 && smem > attr[half]) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
