@@ -912,14 +912,11 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  const int blk = blockIdx.x;
-  const int per_img = prm.blocks_w * prm.blocks_h;
-  // block order: image rows from the bottom up, all images of a row band together. Bands differ a lot in kept
-  // points (upper rows leave the z-range early); with the lightest band last the tail of the last wave is short.
-  const int per_band = prm.bn * prm.blocks_w;
-  const int bh = prm.blocks_h - 1 - blk / per_band;
-  const int brem = blk % per_band;
-  const int bn = brem / prm.blocks_w, bw = brem - bn * prm.blocks_w;
+  // 3-D grid (w-block, image, row band): no integer divisions to find the block. Bands are dispatched from the bottom
+  // of the image up, all images of a band together: bands differ a lot in kept points (upper rows leave the z-range
+  // early) and with the lightest band last the tail of the last wave is short.
+  const int bw = blockIdx.x, bn = blockIdx.y, bh = prm.blocks_h - 1 - (int)blockIdx.z;
+  const int blk = (bh * prm.bn + bn) * prm.blocks_w + bw;   // timeline slot (debug hook only)
   const int h0 = bh * kPixH, w0 = bw * kPixW;
   const int hw = prm.h * prm.w;
   const int64_t img_base = (int64_t)bn * prm.d * hw;
@@ -1281,8 +1278,10 @@ static int backward_joint_launch(const void* og, void* dg, void* fg, const void*
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = smem;
   }
-  launch_pdl(kern, dim3((unsigned)n_blocks), dim3(kBwdThreads), smem, st, (const T*)og, (const T*)depth, (const T*)feat,
-             point_rank, prm, (T*)dg, (T*)fg);
+  (void)n_blocks;
+  if (prm.bn > 65535 || prm.blocks_h > 65535) return BEVPOOL_ERR_OVERFLOW;
+  launch_pdl(kern, dim3((unsigned)prm.blocks_w, (unsigned)prm.bn, (unsigned)prm.blocks_h), dim3(kBwdThreads), smem, st,
+             (const T*)og, (const T*)depth, (const T*)feat, point_rank, prm, (T*)dg, (T*)fg);
   count_launch();
   return launch_status();
 }
