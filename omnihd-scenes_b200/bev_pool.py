@@ -125,6 +125,33 @@ def _find_plan(ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_len
     return plan
 
 
+# Rank tensors that did not come from this package's prepare: the fused forward walks the sorted point list by voxel,
+# which equals "pool exactly the given intervals" only if the intervals are the run-length segmentation of a sorted,
+# in-range ranks_bev. That is verified ON THE DEVICE once per tensor set (one boolean read-back, cached by identity
+# and version like the plans); anything else (a subset of intervals, split intervals, unsorted or out-of-range
+# ranks) takes the reference-contract kernel, which pools precisely the intervals it is given.
+_CANONICAL = {}
+
+
+def _intervals_are_canonical(plan_key, rb, starts, lengths, n_vox):
+    key = id(plan_key[0])
+    hit = _CANONICAL.get(key)
+    if hit is not None and hit[2] == n_vox and all(r() is t and t._version == v for r, t, v in zip(hit[0], plan_key, hit[1])):
+        return hit[3]
+    n, i = rb.numel(), starts.numel()
+    if n == 0 or i == 0:
+        ok = False
+    else:
+        st, ln = starts.long(), lengths.long()
+        heads = rb[st.clamp(0, n - 1)]
+        ok = bool(((rb[1:] >= rb[:-1]).all() & (rb[0] >= 0) & (rb[-1] < n_vox) & (st[0] == 0) &
+                   (st[1:] == st[:-1] + ln[:-1]).all() & (st[-1] + ln[-1] == n) & (ln > 0).all() &
+                   (heads[1:] > heads[:-1]).all()).item())
+    _CANONICAL[key] = ([weakref.ref(t) for t in plan_key], [t._version for t in plan_key], n_vox, ok)
+    weakref.finalize(plan_key[0], _CANONICAL.pop, key, None)
+    return ok
+
+
 # ----------------------------------------------------------------------------- raw launches
 def _launch_forward(depth, feat, out, rd, rf, rb, starts, lengths):
     lib = _lib.load()
@@ -238,13 +265,13 @@ class _BevPoolV2Fused(torch.autograd.Function):
         ctx.plan = _find_plan(*plan_key, depth, feat)
         ctx.shape = (B, Z, Y, X, C)
         ctx.in_dtypes = (in_depth_dtype, in_feat_dtype)
-        # the fused kernel walks voxels in rank order: it needs non-decreasing ranks_bev. Tensors that
-        # came from our prepare are sorted by construction; anything else is checked (one small sync).
+        # the fused kernel walks the sorted point list by voxel. Tensors that came from our prepare are canonical by
+        # construction; anything else is verified on the device (see _intervals_are_canonical).
         fused_ok = C % 4 == 0 and rb.numel() > 0 and feat.data_ptr() % 16 == 0 and \
-            (ctx.plan is not None or bool((rb[1:] >= rb[:-1]).all()))
+            (ctx.plan is not None or _intervals_are_canonical(plan_key, rb, starts, lengths, B * Z * Y * X))
         if not fused_ok:
-            # odd channel counts (the reference's KAT has C=2) or unsorted intervals:
-            # reference-contract kernel + transpose kernel
+            # odd channel counts (the reference's KAT has C=2), or intervals that are not the plain run-length
+            # segmentation of a sorted ranks_bev: reference-contract kernel + transpose kernel
             out_cl = feat.new_zeros((B, Z, Y, X, C))
             _launch_forward(depth, feat, out_cl, rd, rf, rb, starts, lengths)
             out = feat.new_empty((B, C, Z, Y, X))
@@ -299,7 +326,9 @@ class TRTBEVPoolv2(torch.autograd.Function):
         depth, feat, rd, rf, rb, starts, lengths = _canon_inputs(depth, feat, ranks_depth, ranks_feat, ranks_bev,
                                                                  interval_starts, interval_lengths)
         C = feat.shape[-1]
-        if C % 4 != 0 or rb.numel() == 0 or not bool((rb[1:] >= rb[:-1]).all()):
+        key = (ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths)
+        if C % 4 != 0 or rb.numel() == 0 or feat.data_ptr() % 16 != 0 or \
+                not _intervals_are_canonical(key, rb, starts, lengths, out_height * out_width):
             out = feat.new_zeros((1, out_height, out_width, C))
             _launch_forward(depth, feat, out, rd, rf, rb, starts, lengths)
             return out

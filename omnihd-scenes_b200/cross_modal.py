@@ -81,31 +81,60 @@ def gate_concat(a, b, att_for_a, att_for_b):
     return _GateConcat.apply(a, b, att_for_a, att_for_b)
 
 
-class _ConvReLU(nn.Module):
-    """What mmcv's ConvModule(…, norm_cfg=None, act_cfg=ReLU) is: `.conv` (with bias) + ReLU, same state_dict keys."""
+def _build_norm(norm_cfg, channels):
+    """(attribute name, module) the way mmcv's `build_norm_layer` names and builds it (mmcv/cnn/bricks/norm.py):
+    BN / BN2d / SyncBN -> `bn`, GN -> `gn`; `requires_grad` (default True) freezes the affine parameters."""
+    cfg = dict(norm_cfg)
+    kind = cfg.pop("type")
+    requires_grad = cfg.pop("requires_grad", True)
+    cfg.setdefault("eps", 1e-5)
+    if kind in ("BN", "BN2d"):
+        name, layer = "bn", nn.BatchNorm2d(channels, **cfg)
+    elif kind == "SyncBN":
+        name, layer = "bn", nn.SyncBatchNorm(channels, **cfg)
+    elif kind == "GN":
+        name, layer = "gn", nn.GroupNorm(num_channels=channels, **cfg)
+    else:
+        raise ValueError(f"unsupported norm_cfg type {kind!r} (BN, BN2d, SyncBN, GN)")
+    for prm in layer.parameters():
+        prm.requires_grad = requires_grad
+    return name, layer
 
-    def __init__(self, cin, cout, k, padding):
+
+class _ConvModule(nn.Module):
+    """What mmcv's ConvModule(cin, cout, k, padding, conv_cfg=None, norm_cfg=..., act_cfg=ReLU, inplace=False) is,
+    with the same state_dict keys: `.conv` (bias only when there is no norm: mmcv's bias='auto'), the norm layer
+    under mmcv's abbreviation (`.bn` / `.gn`), ReLU; order conv -> norm -> act."""
+
+    def __init__(self, cin, cout, k, padding, norm_cfg=None):
         super().__init__()
-        self.conv = nn.Conv2d(cin, cout, k, padding=padding)
+        self.conv = nn.Conv2d(cin, cout, k, padding=padding, bias=norm_cfg is None)
+        self.norm_name = None
+        if norm_cfg is not None:
+            self.norm_name, layer = _build_norm(norm_cfg, cout)
+            self.add_module(self.norm_name, layer)
         self.activate = nn.ReLU(inplace=False)
 
     def forward(self, x):
-        return self.activate(self.conv(x))
+        x = self.conv(x)
+        if self.norm_name is not None:
+            x = getattr(self, self.norm_name)(x)
+        return self.activate(x)
 
 
 class Cross_Modal_Fusion(nn.Module):
-    """Same constructor, parameter names and forward as the reference class (norm_cfg other than None is not
-    supported: the reference's config passes none)."""
+    """Same constructor, parameter / buffer names and forward as the reference class. The reference detector builds it
+    with `norm_cfg=dict(type='BN', eps=1e-3, momentum=0.01)` (rcfusion_faster_rcnn.py:38,74), i.e. `reduce_mixBEV` is
+    conv(bias=False) + BN + ReLU with keys `reduce_mixBEV.conv.weight`, `reduce_mixBEV.bn.*`; `norm_cfg=None` (the
+    class default) gives conv(bias=True) + ReLU. Channel counts are the reference's 256 + 384 -> 384 by default."""
 
     def __init__(self, kernel_size=3, norm_cfg=None, img_channels=256, radar_channels=384, out_channels=384):
         super().__init__()
         assert kernel_size in (3, 7), 'kernel size must be 3 or 7'
-        if norm_cfg is not None:
-            raise NotImplementedError("norm_cfg: use the reference module for normalised variants")
         padding = 3 if kernel_size == 7 else 1
         self.att_img = nn.Sequential(nn.Conv2d(2, 1, kernel_size, padding=padding, bias=False), nn.Sigmoid())
         self.att_radar = nn.Sequential(nn.Conv2d(2, 1, kernel_size, padding=padding, bias=False), nn.Sigmoid())
-        self.reduce_mixBEV = _ConvReLU(img_channels + radar_channels, out_channels, 3, 1)
+        self.reduce_mixBEV = _ConvModule(img_channels + radar_channels, out_channels, 3, 1, norm_cfg)
 
     def fuse(self, img_bev, radar_bev):
         """Everything up to the 3x3 reduction conv: [N, Ci + Cr, H, W]."""

@@ -1,6 +1,9 @@
 // Library-level entry points: ABI version, error text, launch counter.
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <stdlib.h>
+#include <utility>
 
 #include "common.cuh"
 
@@ -14,6 +17,24 @@ bool pdl_enabled() {
     v = !(e && e[0] == '0');
   }
   return v != 0;
+}
+
+// The opt-in to more than 48 KB of dynamic shared memory is a per-function AND per-device attribute: the cache is
+// keyed by both (one process may drive several GPUs, and distinct instantiations never share an entry).
+int ensure_dynamic_smem_impl(const void* kern, size_t smem) {
+  if (smem <= 48 * 1024) return 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> granted;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = granted[std::make_pair(kern, dev)];
+  if (smem <= have) return 0;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  have = smem;
+  return 0;
 }
 }  // namespace bevpool
 

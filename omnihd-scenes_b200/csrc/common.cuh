@@ -39,6 +39,14 @@ __device__ __forceinline__ void pdl_wait() {
 
 bool pdl_enabled();   // abi.cu (BEVPOOL_PDL=0 disables)
 
+// Opt a kernel in to `smem` bytes of dynamic shared memory (> 48 KB) on the CURRENT device; cached per
+// (kernel, device). Returns 0 or the cudaError_t.
+int ensure_dynamic_smem_impl(const void* kern, size_t smem);   // abi.cu
+template <typename... KArgs>
+inline int ensure_dynamic_smem(void (*kern)(KArgs...), size_t smem) {
+  return ensure_dynamic_smem_impl(reinterpret_cast<const void*>(kern), smem);
+}
+
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};

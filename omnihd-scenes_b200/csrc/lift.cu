@@ -197,19 +197,11 @@ template <typename T, int NV>
 static void lift_launch_nv(bool fwd, const void* a, const void* b, const void* cc_, void* o1, void* o2, int d, int c, int hw,
                            int cl, int64_t bpi, int64_t blocks, size_t smem, cudaStream_t st) {
   if (fwd) {
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-      cudaFuncSetAttribute(lift_fwd_kernel<T, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr = smem;
-    }
+    if (ensure_dynamic_smem(lift_fwd_kernel<T, NV>, smem)) return;   // the failed launch is reported by launch_status()
     launch_pdl(lift_fwd_kernel<T, NV>, dim3((unsigned)blocks), dim3(kLiftThreads), smem, st, (const T*)a, (T*)o1, (T*)o2, d,
                c, hw, cl, bpi);
   } else {
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-      cudaFuncSetAttribute(lift_bwd_kernel<T, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr = smem;
-    }
+    if (ensure_dynamic_smem(lift_bwd_kernel<T, NV>, smem)) return;
     launch_pdl(lift_bwd_kernel<T, NV>, dim3((unsigned)blocks), dim3(kLiftThreads), smem, st, (const T*)a, (const T*)b,
                (const T*)cc_, (T*)o1, d, c, hw, cl, bpi);
   }

@@ -83,11 +83,7 @@ static int pillar_forward_t(const void* feats, const int* coors, void* canvas, i
   if (total > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
   const size_t smem = sizeof(float) * (size_t)c * (kPcCols + 1);
   if (smem > 200 * 1024) return BEVPOOL_ERR_BAD_CHANNELS;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaFuncSetAttribute(pillar_canvas_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = smem;
-  }
+  if (int rc = ensure_dynamic_smem(pillar_canvas_kernel<T>, smem)) return rc;
   launch_pdl(pillar_canvas_kernel<T>, dim3((unsigned)total), dim3(256), smem, st, (const T*)feats, (const int*)pillar_index,
              (T*)canvas, c, cells, tiles);
   count_launch();

@@ -106,67 +106,81 @@ pool_fwd_scalar_kernel(const T* __restrict__ depth, const T* __restrict__ feat, 
 //   depth_grad[rd_i] = <og[rb_i,:], feat[f,:]>      (one butterfly reduction per point)
 //   feat_grad[f,:]   = sum_i depth[rd_i] * og[rb_i,:]
 // The feature row stays in registers for the whole interval; og rows are read exactly once.
-template <typename T>
+// S = channel sweeps of 128 (C <= 128 * S): the pixel's whole feature row and feat_grad row live in registers, so a
+// point's dot product is completed in ONE pass and depth_grad is written exactly once (never re-read, never
+// rounded to the io type between sweeps).
+template <typename T, int S>
 __global__ void __launch_bounds__(kPoolThreads)
 pool_bwd_kernel(const T* __restrict__ og, const T* __restrict__ depth, const T* __restrict__ feat,
                 const int* __restrict__ rd, const int* __restrict__ rf, const int* __restrict__ rb,
                 const int* __restrict__ starts, const int* __restrict__ lengths, int64_t n_intervals, int c,
                 T* __restrict__ depth_grad, T* __restrict__ feat_grad) {
+  constexpr int U = S == 1 ? 4 : (S == 2 ? 2 : 1);   // points in flight per step (register budget)
   const int lane = lane_id();
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int c4 = c >> 2;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t k = warp0; k < n_intervals; k += n_warps) {
     const int s = __ldg(starts + k), len = __ldg(lengths + k);
     const int64_t fbase = (int64_t)__ldg(rf + s) * c;
-    for (int cb = 0; cb < c4; cb += 32) {
-      const int ch = cb + lane;
-      const bool act = ch < c4;
-      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 fv = act ? Vec4<T>::load(feat, fbase + 4 * ch) : zero;
-      float4 fg = zero;
-      for (int base = 0; base < len; base += 32) {
-        int my_rb = 0, my_rd = 0;
-        float my_d = 0.f, my_dg = 0.f;
-        if (base + lane < len) {
-          my_rb = ldg_stream_i32(rb + s + base + lane);
-          my_rd = ldg_stream_i32(rd + s + base + lane);
-          my_d = Vec4<T>::load1(depth, my_rd);
-        }
-        const int n = min(32, len - base);
-        int i = 0;
-        for (; i + 4 <= n; i += 4) {
-          float4 g[4];
-          float d[4], p[4];
+    float4 fv[S], fg[S];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int b = __shfl_sync(kFullMask, my_rb, i + u);
-            d[u] = __shfl_sync(kFullMask, my_d, i + u);
-            g[u] = act ? Vec4<T>::load(og, (int64_t)b * c + 4 * ch) : zero;
-          }
+    for (int q = 0; q < S; ++q) {
+      fv[q] = (32 * q + lane < c4) ? Vec4<T>::load(feat, fbase + 4 * (32 * q + lane)) : zero;
+      fg[q] = zero;
+    }
+    for (int base = 0; base < len; base += 32) {
+      int my_rb = 0, my_rd = 0;
+      float my_d = 0.f, my_dg = 0.f;
+      if (base + lane < len) {
+        my_rb = ldg_stream_i32(rb + s + base + lane);
+        my_rd = ldg_stream_i32(rd + s + base + lane);
+        my_d = Vec4<T>::load1(depth, my_rd);
+      }
+      const int n = min(32, len - base);
+      int i = 0;
+      for (; i + U <= n; i += U) {
+        float4 g[U][S];
+        float d[U];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            fg = fma4(g[u], d[u], fg);
-            p[u] = warp_sum(dot4(g[u], fv, 0.f));
-            if (lane == i + u) my_dg = p[u];
+        for (int u = 0; u < U; ++u) {
+          const int b = __shfl_sync(kFullMask, my_rb, i + u);
+          d[u] = __shfl_sync(kFullMask, my_d, i + u);
+#pragma unroll
+          for (int q = 0; q < S; ++q)
+            g[u][q] = (32 * q + lane < c4) ? Vec4<T>::load(og, (int64_t)b * c + 4 * (32 * q + lane)) : zero;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float dotp = 0.f;
+#pragma unroll
+          for (int q = 0; q < S; ++q) {
+            fg[q] = fma4(g[u][q], d[u], fg[q]);
+            dotp = dot4(g[u][q], fv[q], dotp);
           }
-        }
-        for (; i < n; ++i) {
-          const int b = __shfl_sync(kFullMask, my_rb, i);
-          const float d = __shfl_sync(kFullMask, my_d, i);
-          const float4 g = act ? Vec4<T>::load(og, (int64_t)b * c + 4 * ch) : zero;
-          fg = fma4(g, d, fg);
-          const float p = warp_sum(dot4(g, fv, 0.f));
-          if (lane == i) my_dg = p;
-        }
-        if (base + lane < len) {
-          // with more than 128 channels the dot product is completed over several sweeps
-          if (cb == 0) Vec4<T>::store1(depth_grad, my_rd, my_dg);
-          else Vec4<T>::store1(depth_grad, my_rd, Vec4<T>::load1(depth_grad, my_rd) + my_dg);
+          const float pz = warp_sum(dotp);
+          if (lane == i + u) my_dg = pz;
         }
       }
-      if (act) Vec4<T>::store(feat_grad, fbase + 4 * ch, fg);
+      for (; i < n; ++i) {
+        const int b = __shfl_sync(kFullMask, my_rb, i);
+        const float d = __shfl_sync(kFullMask, my_d, i);
+        float dotp = 0.f;
+#pragma unroll
+        for (int q = 0; q < S; ++q) {
+          const float4 g = (32 * q + lane < c4) ? Vec4<T>::load(og, (int64_t)b * c + 4 * (32 * q + lane)) : zero;
+          fg[q] = fma4(g, d, fg[q]);
+          dotp = dot4(g, fv[q], dotp);
+        }
+        const float pz = warp_sum(dotp);
+        if (lane == i) my_dg = pz;
+      }
+      if (base + lane < len) Vec4<T>::store1(depth_grad, my_rd, my_dg);
     }
+#pragma unroll
+    for (int q = 0; q < S; ++q)
+      if (32 * q + lane < c4) Vec4<T>::store(feat_grad, fbase + 4 * (32 * q + lane), fg[q]);
   }
 }
 
@@ -370,9 +384,11 @@ static int backward_t(const void* og, void* dg, void* fg, const void* depth, con
   if (n_intervals == 0) return 0;
   const int grid = grid_for_warps(n_intervals, kPoolWarps, kNumSMs * 32);
   const bool vec = (c % 4 == 0) && ((uintptr_t)feat % 16 == 0) && ((uintptr_t)og % 16 == 0) && ((uintptr_t)fg % 16 == 0);
-  if (vec)
-    pool_bwd_kernel<T><<<grid, kPoolThreads, 0, st>>>((const T*)og, (const T*)depth, (const T*)feat, rd, rf, rb,
-                                                      starts, lengths, n_intervals, c, (T*)dg, (T*)fg);
+  if (vec && c <= 1024) {
+    auto kern = c <= 128 ? pool_bwd_kernel<T, 1> : (c <= 256 ? pool_bwd_kernel<T, 2> : (c <= 512 ? pool_bwd_kernel<T, 4> : pool_bwd_kernel<T, 8>));
+    kern<<<grid, kPoolThreads, 0, st>>>((const T*)og, (const T*)depth, (const T*)feat, rd, rf, rb,
+                                       starts, lengths, n_intervals, c, (T*)dg, (T*)fg);
+  }
   else
     pool_bwd_scalar_kernel<T><<<grid, kPoolThreads, 0, st>>>((const T*)og, (const T*)depth, (const T*)feat, rd, rf,
                                                              rb, starts, lengths, n_intervals, c, (T*)dg, (T*)fg);
@@ -387,11 +403,7 @@ static int transpose_cl_t(const void* src, void* dst, int b, int c, int64_t cols
   if (total == 0) return 0;
   if (total > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
   const size_t smem = sizeof(float) * (size_t)c * (kTcCols + 1);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaFuncSetAttribute(transpose_to_channels_last_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = smem;
-  }
+  if (int rc = ensure_dynamic_smem(transpose_to_channels_last_kernel<T>, smem)) return rc;
   launch_pdl(transpose_to_channels_last_kernel<T>, dim3((unsigned)total), dim3(256), smem, st, (const T*)src, (T*)dst, c, cols,
              tiles_per_batch);
   count_launch();

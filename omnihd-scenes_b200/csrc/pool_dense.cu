@@ -1184,12 +1184,9 @@ static int forward_tile_t(const void* depth, const void* feat, void* out, const 
     minb = e ? atoi(e) : 2;
   }
   auto kern = minb >= 2 ? pool_fwd_tile_kernel<T, LAYOUT, 2> : pool_fwd_tile_kernel<T, LAYOUT, 1>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    const int max_smem = (int)(sizeof(float) * (128 * kTileStride + kMaxItems * 2 * 128));
-    cudaFuncSetAttribute(pool_fwd_tile_kernel<T, LAYOUT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(pool_fwd_tile_kernel<T, LAYOUT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    attr_set = true;
+  {
+    const size_t max_smem = sizeof(float) * (128 * kTileStride + kMaxItems * 2 * 128);
+    if (int rc = ensure_dynamic_smem(kern, max_smem)) return rc;
   }
   static int warps = 0, cpw = 0;
   if (!warps) {  // tuning knobs (defaults are the measured best on B200)
@@ -1246,11 +1243,7 @@ static int forward_stream_t(const void* depth, const void* feat, void* out, cons
   if (layout == BEVPOOL_LAYOUT_BCZYX) {
     const int64_t tpf = (vpf + kTcCols - 1) / kTcCols;
     const size_t smem2 = sizeof(float) * (size_t)prm.c * (kTcCols + 1);
-    static size_t attr2 = 0;
-    if (smem2 > 48 * 1024 && smem2 > attr2) {
-      cudaFuncSetAttribute(cl_to_bczyx_zero_fill_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-      attr2 = smem2;
-    }
+    if (int rc = ensure_dynamic_smem(cl_to_bczyx_zero_fill_kernel<T>, smem2)) return rc;
     launch_pdl(cl_to_bczyx_zero_fill_kernel<T>, dim3((unsigned)(tpf * prm.frames)), dim3(256), smem2, st, (const T*)scratch,
                vox_pt, (T*)out, prm.c, vpf, tpf);
   } else {
@@ -1273,11 +1266,7 @@ static int backward_joint_launch(const void* og, void* dg, void* fg, const void*
   const size_t smem = d_pad * kPixW * (3 * 16 + 4) + part_bytes;
   if (smem > 200 * 1024) return BEVPOOL_ERR_BAD_ARG;
   auto kern = pool_bwd_joint_kernel<T, CH4>;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = smem;
-  }
+  if (int rc = ensure_dynamic_smem(kern, smem)) return rc;
   (void)n_blocks;
   if (prm.bn > 65535 || prm.blocks_h > 65535) return BEVPOOL_ERR_OVERFLOW;
   launch_pdl(kern, dim3((unsigned)prm.blocks_w, (unsigned)prm.bn, (unsigned)prm.blocks_h), dim3(kBwdThreads), smem, st,
@@ -1323,11 +1312,7 @@ static int backward_block_t(const void* og, void* dg, void* fg, const void* dept
   auto kern = !half ? pool_bwd_block_kernel<T>
                     : (prm.c == 64 ? pool_bwd_block_half_kernel<T, 64>
                                    : (prm.c == 32 ? pool_bwd_block_half_kernel<T, 32> : pool_bwd_block_half_kernel<T, 0>));
-  static size_t attr[2] = {0, 0};
-  if (smem > 48 * 1024 && smem > attr[half]) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr[half] = smem;
-  }
+  if (int rc = ensure_dynamic_smem(kern, smem)) return rc;
   kern<<<(unsigned)n_blocks, kBwdThreads, smem, st>>>((const T*)og, (const T*)depth, (const T*)feat, point_rank, prm,
                                                        (T*)dg, (T*)fg);
   count_launch();

@@ -280,11 +280,7 @@ template <typename T, int CH4, int HALVES>
 static void scatter_launch_h(const void* depth, const void* feat, const float* frustum, const float* rots, const float* trans,
                              const ScatterParams& prm, int32_t* point_rank, float* acc, unsigned blocks, size_t smem,
                              cudaStream_t st) {
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaFuncSetAttribute(view_fwd_scatter_kernel<T, CH4, HALVES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = smem;
-  }
+  if (ensure_dynamic_smem(view_fwd_scatter_kernel<T, CH4, HALVES>, smem)) return;   // reported by launch_status()
   (void)blocks;
   launch_pdl(view_fwd_scatter_kernel<T, CH4, HALVES>, dim3((unsigned)prm.blocks_w, (unsigned)prm.blocks_h, (unsigned)prm.bn),
              dim3(kScThreads), smem, st, (const T*)depth, (const T*)feat, frustum, rots, trans, prm, point_rank, acc);
@@ -345,11 +341,7 @@ static int view_forward_t(const void* depth, const void* feat, const float* frus
   if (total > INT32_MAX) return BEVPOOL_ERR_OVERFLOW;
   if (total > 0) {
     const size_t sm = sizeof(float) * (size_t)prm.c * (kAlCols + 1);
-    static size_t attr = 0;
-    if (sm > 48 * 1024 && sm > attr) {
-      cudaFuncSetAttribute(acc_layout_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-      attr = sm;
-    }
+    if (int rc = ensure_dynamic_smem(acc_layout_kernel<T>, sm)) return rc;
     launch_pdl(acc_layout_kernel<T>, dim3((unsigned)total), dim3(256), sm, st, (const float*)acc, (T*)out, prm.c, vpf,
                tiles_per_frame);
     count_launch();

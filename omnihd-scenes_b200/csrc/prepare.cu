@@ -618,11 +618,8 @@ extern "C" int bevpool_prepare_v2(const float* coor, const float* frustum, const
                                                                             point_rank, w.hist0, w.totals, counts_dev);
   } else {
     const size_t cam_smem = sizeof(float) * 12 * (size_t)gd.bn;
-    static size_t attr = 0;
-    if (cam_smem + 9 * 1024 > 48 * 1024 && cam_smem > attr) {
-      cudaFuncSetAttribute(point_rank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cam_smem);
-      attr = cam_smem;
-    }
+    // ~9 KB of static shared memory on top of the camera table: opt in as soon as the TOTAL passes 48 KB
+    if (int rc = ensure_dynamic_smem(point_rank_kernel<false>, cam_smem + 9 * 1024)) return rc;
     point_rank_kernel<false><<<(unsigned)plan.n_tiles, kSortThreads, cam_smem, st>>>(
         coor, frustum, rots, trans, gd, plan, point_rank, w.hist0, w.totals, counts_dev);
   }

@@ -268,17 +268,21 @@ class _FusedViewPool(torch.autograd.Function):
                                                n * planes, rows, layout)
             saved.append((pr, feat_cl))
         fork.join()
-        ctx.saved, ctx.dims, ctx.groups, ctx.feat_cl, ctx.s2c = saved, (B, N, C, D, H, W, X, Y, Z), groups, feat_channels_last, s2c
-        ctx.save_for_backward(depth)
+        ctx.dims, ctx.groups, ctx.feat_cl, ctx.s2c = (B, N, C, D, H, W, X, Y, Z), groups, feat_channels_last, s2c
+        # everything the backward reads goes through save_for_backward: with feat_channels_last the per-group
+        # feature tensors are VIEWS of the caller's input, and autograd's version check must catch an in-place edit
+        ctx.save_for_backward(depth, *[fc for _, fc in saved], *[pr.point_rank for pr, _ in saved])
+        ctx.bn = [pr.bn for pr, _ in saved]
         return out.permute(0, 4, 1, 2, 3) if cl_out else out
 
     @staticmethod
     def backward(ctx, out_grad):
-        (depth,) = ctx.saved_tensors
+        depth = ctx.saved_tensors[0]
         B, N, C, D, H, W, X, Y, Z = ctx.dims
         groups = ctx.groups
+        feat_cls, point_ranks = ctx.saved_tensors[1:1 + groups], ctx.saved_tensors[1 + groups:1 + 2 * groups]
         n = B // groups
-        dt = ctx.saved[0][1].dtype
+        dt = feat_cls[0].dtype
         # a channels_last_3d gradient ([B,Z,Y,X,C] in memory) is consumed as it is; anything else is transposed
         og_is_cl = (not ctx.s2c) and out_grad.dim() == 5 and out_grad.permute(0, 2, 3, 4, 1).is_contiguous()
         out_grad = (out_grad.permute(0, 2, 3, 4, 1) if og_is_cl else out_grad.contiguous()).to(dt)
@@ -288,7 +292,7 @@ class _FusedViewPool(torch.autograd.Function):
         fork = _Fork(depth.device, groups)
         for g, st in enumerate(fork.streams):
             sl = slice(g * n, (g + 1) * n)
-            pr, feat_cl = ctx.saved[g]
+            feat_cl, point_rank, bn = feat_cls[g], point_ranks[g], ctx.bn[g]
             with torch.cuda.stream(st):
                 og_cl = out_grad[sl] if og_is_cl else out_grad.new_empty((n, Z, Y, X, C))
                 if og_is_cl:
@@ -298,7 +302,7 @@ class _FusedViewPool(torch.autograd.Function):
                 else:
                     _launch_transpose(out_grad[sl], og_cl, n, C, Z * Y * X, True)
                 _lib.check(lib.bevpool_v2_backward_dense(_ptr(og_cl), _ptr(depth_grad[sl]), _ptr(feat_grad[sl]),
-                                                         _ptr(depth[sl]), _ptr(feat_cl), _ptr(pr.point_rank), pr.bn, D, H,
+                                                         _ptr(depth[sl]), _ptr(feat_cl), _ptr(point_rank), bn, D, H,
                                                          W, C, 0 if ctx.feat_cl else 1, _column_hint(Z),
                                                          _dtype_code(feat_cl), _stream()),
                            "bevpool_v2_backward_dense")

@@ -253,6 +253,38 @@ def test_forward_long_intervals_and_garbage_output_buffer(pkg, orc):
     assert int((bev != 0).any(dim=1).sum()) == lens.size
 
 
+def test_forward_pools_exactly_the_given_intervals(pkg, orc):
+    """The reference kernel pools the intervals it is handed (bev_pool_cuda.cu:30-47): a SUBSET of the intervals, or
+    intervals cut in two (the later piece overwrites the voxel), must give what the oracle gives for the same
+    arrays — the fused voxel-walk must not be taken for them; out-of-range ranks never reach the fused path."""
+    depth, feat_cl, (rb, rd, rf, st, ln), shape = _forward_cases(pkg, orc, "bevdet_r50_b8", 1)
+    t = [cu(a) for a in (depth, feat_cl, rd, rf, rb)]
+    # (a) every other interval only
+    st_a, ln_a = st[::2].copy(), ln[::2].copy()
+    ref = orc.bev_pool_v2_forward(depth, feat_cl, rd, rf, rb, shape, st_a, ln_a, exact=True)
+    bev = pkg.bev_pool_v2(*t, shape, cu(st_a), cu(ln_a))
+    assert rel_to_max(bev.permute(0, 2, 3, 4, 1).cpu().numpy(), ref) <= TOL
+    trt = pkg.TRTBEVPoolv2.apply(t[0][0], t[1][0], t[2], t[3], t[4], cu(st_a), cu(ln_a), shape[2], shape[3])
+    assert rel_to_max(trt.cpu().numpy()[0], ref[0, 0]) <= TOL
+    # (b) the longest interval cut in two: both pieces write the same voxel (a race in the reference kernel too, one
+    #     thread per interval and channel) — that voxel must hold ONE of the two partial sums, all others the full sum
+    k = int(np.argmax(ln))
+    assert ln[k] >= 2
+    st_b = np.concatenate([st[:k + 1], [st[k] + ln[k] // 2], st[k + 1:]]).astype(np.int32)
+    ln_b = np.concatenate([ln[:k], [ln[k] // 2, ln[k] - ln[k] // 2], ln[k + 1:]]).astype(np.int32)
+    full = orc.bev_pool_v2_forward(depth, feat_cl, rd, rf, rb, shape, st, ln, exact=True)
+    bev_b = pkg.bev_pool_v2(*t, shape, cu(st_b), cu(ln_b)).permute(0, 2, 3, 4, 1).cpu().numpy()
+    vox = np.unravel_index(rb[st[k]], shape[:4])
+    halves = [orc.bev_pool_v2_forward(depth, feat_cl, rd, rf, rb, shape, st_b[j:j + 1], ln_b[j:j + 1], exact=True)[vox]
+              for j in (k, k + 1)]
+    assert min(rel_to_max(bev_b[vox], h) for h in halves) <= TOL
+    bev_b[vox] = full[vox]
+    assert rel_to_max(bev_b, full) <= TOL                        # every other voxel is the full result
+    # (c) canonical intervals passed as fresh tensors (no plan attached) still take the fused walk and agree
+    bev_c = pkg.bev_pool_v2(*t, shape, cu(st), cu(ln))
+    assert rel_to_max(bev_c.permute(0, 2, 3, 4, 1).cpu().numpy(), full) <= TOL
+
+
 def test_forward_matches_reference_cuda_kernel_bitwise(pkg, orc):
     """The reference's unmodified bev_pool_cuda.cu compiled for sm_100a (oracle/_ref) on the same inputs."""
     path = os.path.join(ROOT, "oracle", "_ref", "libref_bevpool_v2.so")
@@ -309,21 +341,24 @@ def test_backward_general_path_vs_oracle(pkg, orc, case):
         assert rel_to_max(f.grad.cpu().numpy(), gf) <= TOL
 
 
-@pytest.mark.parametrize("cfg_name,B", [("bevdet_r50_b8", 8), ("occ_200x200x16_b64", 2), ("bevdepth_hires_b16", 1),
-                                        ("rcfusion_omnihd_b32", 1)])
-def test_view_transform_fwd_bwd_vs_oracle(pkg, orc, cfg_name, B):
-    """Public API end to end at BASELINE sizes: get_geometry -> voxel_pooling_v2 (prepare + bev_pool_v2 with
-    the sort-free backward) and the fully fused module forward; both against the float64 oracle."""
-    cfg = pkg.synthetic.CONFIGS[cfg_name]
-    view, rots, trans, coor, (rb, rd, rf, st, ln), depth, feat, gout = synth_pool_case(pkg, orc, cfg, B)
+def _view_modes_vs_oracle(pkg, orc, cfg, B, dt, modes, seed=0):
+    """Run the public view-transform paths in dtype `dt` and compare with the float64 oracle fed the SAME
+    (dt-rounded) inputs. fp32: 1e-5 of max (north_star); bf16: 2^-8 of max (one output rounding,
+    fp32 accumulation inside)."""
+    view, rots, trans, coor, (rb, rd, rf, st, ln), depth, feat, gout = synth_pool_case(pkg, orc, cfg, B, seed)
+    tol = TOL if dt == torch.float32 else TOL_BF16
+    depth, feat, gout = (t.to(dt) for t in (depth, feat, gout))
+    dq, fq, gq = depth.float(), feat.float(), gout.float()           # what the kernels actually read
     X, Y, Z = (int(v) for v in view.nx)
     C = cfg.channels
-    feat_cl = feat.permute(0, 1, 3, 4, 2).contiguous().numpy()
-    ref = orc.bev_pool_v2_forward(depth.numpy(), feat_cl, rd, rf, rb, (B, Z, Y, X, C), st, ln, exact=True)
-    gd, gf = orc.bev_pool_v2_backward(gout.permute(0, 2, 3, 4, 1).contiguous().numpy(), depth.numpy(), feat_cl,
+    feat_cl = fq.permute(0, 1, 3, 4, 2).contiguous().numpy()
+    ref = orc.bev_pool_v2_forward(dq.numpy(), feat_cl, rd, rf, rb, (B, Z, Y, X, C), st, ln, exact=True)
+    gd, gf = orc.bev_pool_v2_backward(gq.permute(0, 2, 3, 4, 1).contiguous().numpy(), dq.numpy(), feat_cl,
                                       rd, rf, rb, exact=True)
+    rank = orc.voxel_rank(coor, view.dx.numpy(), view.bx.numpy(), view.nx.numpy())
+    dropped = torch.from_numpy(rank < 0).to(DEV)
     view = view.to(DEV)
-    for mode in ("api", "fused", "fused_groups", "fused_sorted", "fused_sorted_groups"):
+    for mode in modes:
         d = depth.to(DEV).requires_grad_()
         f = feat.to(DEV).requires_grad_()
         view.frame_groups = 1
@@ -334,14 +369,56 @@ def test_view_transform_fwd_bwd_vs_oracle(pkg, orc, cfg_name, B):
             if mode.endswith("groups"):      # independent frame groups on concurrent streams
                 view.frame_groups = 2 if B % 2 == 0 else 1
             bev = view(d, f, rots.to(DEV), trans.to(DEV))
-        assert bev.shape == (B, C, Z, Y, X)
-        assert rel_to_max(bev.detach().permute(0, 2, 3, 4, 1).cpu().numpy(), ref) <= TOL, mode
+        assert bev.shape == (B, C, Z, Y, X) and bev.dtype == dt
+        assert rel_to_max(bev.detach().float().permute(0, 2, 3, 4, 1).cpu().numpy(), ref) <= tol, mode
         bev.backward(gout.to(DEV))
-        assert rel_to_max(d.grad.cpu().numpy(), gd) <= TOL, mode
-        assert rel_to_max(f.grad.permute(0, 1, 3, 4, 2).cpu().numpy(), gf) <= TOL, mode
+        assert d.grad.dtype == dt and f.grad.dtype == dt
+        assert rel_to_max(d.grad.float().cpu().numpy(), gd) <= tol, mode
+        assert rel_to_max(f.grad.float().permute(0, 1, 3, 4, 2).cpu().numpy(), gf) <= tol, mode
         # dropped points get exactly zero depth gradient
-        rank = orc.voxel_rank(coor, view.dx.numpy(), view.bx.numpy(), view.nx.numpy())
-        assert float(d.grad.reshape(-1)[torch.from_numpy(rank < 0).to(DEV)].abs().max()) == 0.0
+        assert float(d.grad.reshape(-1)[dropped].abs().max()) == 0.0
+
+
+ALL_MODES = ("api", "fused", "fused_groups", "fused_sorted", "fused_sorted_groups")
+
+
+@pytest.mark.parametrize("cfg_name,B", [("bevdet_r50_b8", 8), ("occ_200x200x16_b64", 2), ("bevdepth_hires_b16", 1),
+                                        ("rcfusion_omnihd_b32", 1)])
+def test_view_transform_fwd_bwd_vs_oracle(pkg, orc, cfg_name, B):
+    """Public API end to end at BASELINE sizes: get_geometry -> voxel_pooling_v2 (prepare + bev_pool_v2 with
+    the sort-free backward) and the fully fused module forward; both against the float64 oracle, in the dtype the
+    config names (cfg 3 is bf16 — the kernels bench.py runs for it)."""
+    cfg = pkg.synthetic.CONFIGS[cfg_name]
+    dt = torch.bfloat16 if cfg.dtype == "bf16" else torch.float32
+    _view_modes_vs_oracle(pkg, orc, cfg, B, dt, ALL_MODES)
+
+
+def _bf16_cases(pkg):
+    import dataclasses
+    C = pkg.synthetic.CONFIGS
+    return {
+        # cfg 3 shapes (C = 80, Z = 1, D = 118, 32 x 88 features): view_fwd<bf16,20>, acc_layout<bf16>, joint<bf16,20>
+        "hires_b2": (C["bevdepth_hires_b16"], 2),
+        # cfg 2 shapes in bf16, 4 frames (frame groups of 2)
+        "r50_b4": (dataclasses.replace(C["bevdet_r50_b8"], dtype="bf16"), 4),
+        # C = 64 on a Z = 16 grid (RCFusion grid, smaller image): block_half<bf16,64> backward, two lane groups forward
+        "omnihd_small": (dataclasses.replace(C["rcfusion_omnihd_b32"], final_dim=(136, 240), dtype="bf16"), 2),
+        # C = 32 on the occupancy grid: block_half<bf16,32>, four lane groups
+        "occ_b2": (dataclasses.replace(C["occ_200x200x16_b64"], dtype="bf16"), 2),
+        # C = 32 / 64 / 128 on a Z = 1 grid: the other joint-backward instantiations
+        "r50_c32": (dataclasses.replace(C["bevdet_r50_b8"], channels=32, dtype="bf16"), 2),
+        "r50_c64": (dataclasses.replace(C["bevdet_r50_b8"], channels=64, dtype="bf16"), 2),
+        "r50_c128": (dataclasses.replace(C["bevdet_r50_b8"], channels=128, dtype="bf16"), 2),
+    }
+
+
+@pytest.mark.parametrize("case", ["hires_b2", "r50_b4", "omnihd_small", "occ_b2", "r50_c32", "r50_c64", "r50_c128"])
+def test_fused_path_bf16_vs_oracle(pkg, orc, case):
+    """bf16 in / bf16 out through the FUSED module path (the kernels bench.py times for cfg 3) and the API
+    sequence, frame groups 1 and 2, both `deterministic` settings: forward and both gradients against the float64
+    oracle fed the bf16-rounded inputs, tolerance 2^-8 of max|ref|."""
+    cfg, B = _bf16_cases(pkg)[case]
+    _view_modes_vs_oracle(pkg, orc, cfg, B, torch.bfloat16, ALL_MODES, seed=3)
 
 
 def test_linearity_and_checksum_full_size(pkg):

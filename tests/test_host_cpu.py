@@ -169,3 +169,33 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["e2e"]["value"] == line["value"]
+
+
+def test_cross_modal_state_dict_keys_match_reference_construction(pkg):
+    """The reference detector builds Cross_Modal_Fusion(kernel_size=3, norm_cfg=dict(type='BN', eps=1e-3,
+    momentum=0.01)) (rcfusion_faster_rcnn.py:38,74), so `reduce_mixBEV` is mmcv ConvModule = conv(bias=False) + BN +
+    ReLU with keys conv.weight / bn.* (mmcv v1.4.0 conv_module.py: bias='auto' -> not with_norm; norm name from
+    build_norm_layer's abbreviation 'bn'). norm_cfg=None (the class default) keeps the conv bias."""
+    cm = pkg.cross_modal
+    m = cm.Cross_Modal_Fusion(kernel_size=3, norm_cfg=dict(type='BN', eps=1e-3, momentum=0.01))
+    assert sorted(m.state_dict()) == sorted([
+        'att_img.0.weight', 'att_radar.0.weight', 'reduce_mixBEV.conv.weight', 'reduce_mixBEV.bn.weight',
+        'reduce_mixBEV.bn.bias', 'reduce_mixBEV.bn.running_mean', 'reduce_mixBEV.bn.running_var',
+        'reduce_mixBEV.bn.num_batches_tracked'])
+    assert tuple(m.state_dict()['reduce_mixBEV.conv.weight'].shape) == (384, 640, 3, 3)
+    assert m.reduce_mixBEV.bn.eps == 1e-3 and m.reduce_mixBEV.bn.momentum == 0.01
+    plain = cm.Cross_Modal_Fusion(kernel_size=7)
+    assert sorted(plain.state_dict()) == ['att_img.0.weight', 'att_radar.0.weight', 'reduce_mixBEV.conv.bias',
+                                          'reduce_mixBEV.conv.weight']
+    assert tuple(plain.att_img[0].weight.shape) == (1, 2, 7, 7)
+    sync = cm.Cross_Modal_Fusion(norm_cfg=dict(type='SyncBN', requires_grad=False), img_channels=4, radar_channels=4,
+                                 out_channels=4)
+    assert isinstance(sync.reduce_mixBEV.bn, torch.nn.SyncBatchNorm) and not sync.reduce_mixBEV.bn.weight.requires_grad
+    with pytest.raises(ValueError):
+        cm.Cross_Modal_Fusion(norm_cfg=dict(type='LN'))
+    # the BN module in eval mode is conv + affine + relu of the fused glue output (CPU-checkable part)
+    x = torch.randn(2, 8, 5, 7)
+    ref = torch.relu(torch.nn.functional.batch_norm(sync.reduce_mixBEV.conv(x), sync.reduce_mixBEV.bn.running_mean,
+                                                    sync.reduce_mixBEV.bn.running_var, sync.reduce_mixBEV.bn.weight,
+                                                    sync.reduce_mixBEV.bn.bias, False, 0.0, sync.reduce_mixBEV.bn.eps))
+    assert torch.allclose(sync.reduce_mixBEV.eval()(x), ref)
