@@ -340,6 +340,22 @@ class LSSViewTransform(nn.Module):
         return cls(final_dim, downsample, camera_depth_range, (pc_range[0], pc_range[3], grid),
                    (pc_range[1], pc_range[4], grid), (pc_range[2], pc_range[5], grid))
 
+    @classmethod
+    def adopt(cls, frustum, dx, bx, nx, frame_groups=1, deterministic=False):
+        """View transform over an EXISTING module's state (plugin.patch_lss_class): shares the reference module's
+        `frustum` Parameter ([D, fH, fW, 3], cam_stream_lss_bevpoolv2.py:216-227) and its `dx / bx / nx` tensors
+        (:77-82) instead of rebuilding them, so values set by hand on the reference module are honoured."""
+        self = cls.__new__(cls)
+        nn.Module.__init__(self)
+        self.frame_groups, self.deterministic = frame_groups, deterministic
+        self.final_dim = self.downsample = self.grid_conf = None
+        self.dx = torch.as_tensor(dx).detach().float().cpu()
+        self.bx = torch.as_tensor(bx).detach().float().cpu()
+        self.nx = torch.as_tensor(nx).detach().long().cpu()
+        self.__dict__["frustum"] = frustum          # shared, not re-registered: the owner's state_dict is unchanged
+        self.D, self.fH, self.fW = (int(v) for v in frustum.shape[:3])
+        return self
+
     # -- reference method names -------------------------------------------------------------
     def get_geometry(self, rots, trans, post_rots=None, post_trans=None, extra_rots=None, extra_trans=None):
         if any(v is not None for v in (post_rots, post_trans, extra_rots, extra_trans)):

@@ -1,0 +1,203 @@
+"""GPU (-m gpu): the drop-in is exercised against the reference's UNMODIFIED Python classes.
+
+The reference files are imported as they are (oracle/refimport.py: from oracle/_ref/py staged by `make -C oracle refpy`,
+or from /root/reference in the build container); only mmcv / mmdet3d / matplotlib are stubbed. Three levels:
+
+  * the reference's own `bev_pool.py` (QuickCumsumCuda, bev_pool_v2, TRTBEVPoolv2 and its KAT `test_bev_pool_v2`) on the
+    ctypes binding `bev_pool_v2_ext`                                    -> plugin.install_ext()
+  * the reference's `LiftSplatShoot.voxel_pooling_v2 / get_voxels` with this package's operator module and the two patched
+    methods (`get_geometry`, `voxel_pooling_prepare_v2`)                                   -> plugin.install() + patch_lss_class(fused=False)
+  * the same class with `get_voxels` routed to the fused view transform (zero source edits)   -> patch_lss_class()
+
+All results are compared with the float64 oracle (1e-5 of max) and ranks with the reference's own torch-op prepare.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, rel_to_max
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def refimport():
+    sys.path.insert(0, ROOT)
+    from oracle import refimport as ri
+    if ri.ref_root() is None:
+        pytest.skip("reference Python files not staged (make -C oracle refpy) and /root/reference absent")
+    return ri
+
+
+def _cleanup(ri):
+    for name in list(sys.modules):
+        if name.startswith("projects.mmdet3d_plugin"):
+            del sys.modules[name]
+
+
+CASE = dict(final_dim=(64, 176), downsample=8, dbound=(1.0, 60.0, 1.0), xb=(-51.2, 51.2, 0.8), yb=(-51.2, 51.2, 0.8),
+            zb=(-5.0, 3.0, 8.0))
+CASE_Z = dict(final_dim=(64, 176), downsample=8, dbound=(1.0, 45.0, 0.5), xb=(-40.0, 40.0, 0.4), yb=(-40.0, 40.0, 0.4),
+              zb=(-1.0, 5.4, 0.4))
+
+
+def _oracle_case(orc, lss, rots, trans, depth, feat, gout):
+    """float64 forward / backward of the pooling given (depth, feat) as numpy, through the oracle's own prepare."""
+    coor = orc.get_geometry(lss.frustum.detach().cpu().numpy(), rots.numpy(), trans.numpy())
+    dx, bx, nx = lss.dx.cpu().numpy(), lss.bx.cpu().numpy(), lss.nx.cpu().numpy()
+    rb, rd, rf, st, ln = orc.prepare_v2(coor, dx, bx, nx)
+    B = depth.shape[0]
+    X, Y, Z = (int(v) for v in nx)
+    C = feat.shape[2]
+    feat_cl = np.ascontiguousarray(feat.transpose(0, 1, 3, 4, 2))
+    ref = orc.bev_pool_v2_forward(depth, feat_cl, rd, rf, rb, (B, Z, Y, X, C), st, ln, exact=True)
+    gd, gf = orc.bev_pool_v2_backward(np.ascontiguousarray(gout.transpose(0, 2, 3, 4, 1)), depth, feat_cl, rd, rf, rb,
+                                      exact=True)
+    return coor, (rb, rd, rf, st, ln), ref, gd, gf.transpose(0, 1, 4, 2, 3)
+
+
+@pytest.mark.parametrize("case", [CASE, CASE_Z])
+def test_unmodified_reference_lss_with_patched_methods(pkg, orc, refimport, case):
+    """LiftSplatShoot (cam_stream_lss_bevpoolv2.py:149-375), unmodified: get_voxels / voxel_pooling_v2 through (a) the
+    reference's own call sequence on our kernels and (b) the fused route, vs the oracle; its own torch-op prepare
+    (run on the same GPU) vs ours, bit for bit."""
+    _cleanup(refimport)
+    pkg.plugin.install(force=True)
+    ref = refimport.import_reference_lss("bevfusion")
+    assert ref.bev_pool_v2 is pkg.bev_pool_v2                 # bound at import time from the registered module
+    torch.manual_seed(0)
+    lss = refimport.make_reference_lss(ref, case["final_dim"], case["downsample"], case["dbound"], case["xb"], case["yb"],
+                                       case["zb"], inputC=8, camC=8).to(DEV)
+    keys_before = sorted(lss.state_dict())
+    B, N = 2, 6
+    rots, trans = pkg.synthetic.camera_ring(B, N, case["final_dim"], seed=2)
+    x_in = torch.randn(B, N, 8, lss.fH, lss.fW, device=DEV)
+    X, Y, Z = (int(v) for v in lss.nx)
+    gout = torch.randn(B, 8, Z, Y, X, device=DEV)
+
+    # the reference's own torch-op geometry + prepare on this GPU (unpatched class)
+    with torch.no_grad():
+        coor_ref = lss.get_geometry(rots.to(DEV), trans.to(DEV))
+        ranks_ref = lss.voxel_pooling_prepare_v2(coor_ref)
+        feat0, depth0 = lss.get_cam_feats(x_in)
+    coor, ranks, want, gd, gf = _oracle_case(orc, lss, rots, trans, depth0.cpu().numpy(), feat0.cpu().numpy(),
+                                             gout.cpu().numpy())
+    # gradient w.r.t. the module input through the reference's own torch graph, fed the oracle's pooling gradients
+    x_chk = x_in.clone().requires_grad_()
+    f_chk, d_chk = lss.get_cam_feats(x_chk)
+    torch.autograd.backward([d_chk, f_chk], [torch.from_numpy(gd).to(DEV).float(), torch.from_numpy(gf.copy()).to(DEV).float()])
+
+    for fused in (False, True):
+        pkg.plugin.patch_lss_class(ref.LiftSplatShoot, fused=fused)
+        # geometry and prepare: ours vs the reference's own GPU result and vs the oracle
+        got_coor = lss.get_geometry(rots.to(DEV), trans.to(DEV))
+        assert np.array_equal(got_coor.cpu().numpy(), coor)
+        got = lss.voxel_pooling_prepare_v2(got_coor)
+        for a, b, r, key in zip(got, ranks, ranks_ref, ("ranks_bev", "ranks_depth", "ranks_feat", "starts", "lengths")):
+            assert a.dtype == torch.int32 and np.array_equal(a.cpu().numpy(), b), key
+            if key in ("ranks_bev", "starts", "lengths"):       # order-independent outputs of the reference's CUDA argsort
+                assert torch.equal(a, r), key
+        if np.array_equal(coor_ref.cpu().numpy(), coor):   # cuBLAS bmm may differ from the CPU bits
+            o = np.lexsort((ranks_ref[1].cpu().numpy(), ranks_ref[0].cpu().numpy()))
+            assert np.array_equal(ranks_ref[1].cpu().numpy()[o], ranks[1])
+        x = x_in.clone().requires_grad_()
+        bev, depth = lss.get_voxels(x, rots.to(DEV), trans.to(DEV))
+        assert bev.shape == (B, 8, Z, Y, X) and depth.shape == (B, N, lss.D, lss.fH, lss.fW)
+        assert rel_to_max(bev.detach().permute(0, 2, 3, 4, 1).cpu().numpy(), want) <= TOL, fused
+        bev.backward(gout)
+        assert rel_to_max(x.grad.cpu().numpy(), x_chk.grad.cpu().numpy()) <= TOL, fused
+        assert lss.s2c(bev).shape == (B, Z * 8, Y, X)
+        assert sorted(lss.state_dict()) == keys_before            # nothing was registered on the reference module
+        pkg.plugin.unpatch_lss_class(ref.LiftSplatShoot)
+    assert ref.LiftSplatShoot.get_voxels is not None and not hasattr(ref.LiftSplatShoot, "_bevpool_b200_orig_get_voxels")
+    _cleanup(refimport)
+
+
+@pytest.mark.parametrize("variant", ["rcfusion_depth", "bevfusion_depth"])
+def test_unmodified_depthnet_variants_voxel_pooling(pkg, orc, refimport, variant):
+    """LiftSplatShoot_Depth (…_depthnet.py:269-350, both copies) cannot be CONSTRUCTED without mmcv (DCN, build_norm_layer),
+    but its view-transform methods only read dx / bx / nx / frustum: they are run unmodified on a bare instance. This
+    variant moves nx to the GPU, so bev_feat_shape carries 0-dim CUDA tensors (:278-282)."""
+    _cleanup(refimport)
+    pkg.plugin.install(force=True)
+    ref = refimport.import_reference_lss(variant)
+    cls = ref.LiftSplatShoot_Depth
+    lss = cls.__new__(cls)
+    torch.nn.Module.__init__(lss)
+    cfg = pkg.synthetic.ViewConfig("dv", (64, 176), 8, (1.0, 60.0, 1.0), (-60.0, 60.0, 0.5), (-40.0, 40.0, 0.5), (-3.0, 5.0, 0.5),
+                                   8, 2)
+    lss.dx, lss.bx, lss.nx = ref.gen_dx_bx(list(cfg.xbound), list(cfg.ybound), list(cfg.zbound))
+    lss.frustum = torch.nn.Parameter(pkg.create_frustum(cfg.final_dim, cfg.downsample, cfg.dbound).to(DEV), requires_grad=False)
+    lss.D, lss.camC = cfg.D, cfg.channels
+    B, N = cfg.batch, cfg.n_cams
+    rots, trans = pkg.synthetic.camera_ring(B, N, cfg.final_dim, seed=4)
+    depth, feat, gout = pkg.synthetic.pool_inputs(cfg, seed=4)
+    coor, ranks, want, gd, gf = _oracle_case(orc, lss, rots, trans, depth.numpy(), feat.numpy(), gout.numpy())
+    for fused in (False, True):
+        pkg.plugin.patch_lss_class(cls, fused=fused)
+        d = depth.to(DEV).requires_grad_()
+        f = feat.to(DEV).requires_grad_()
+        lss.__dict__["get_cam_feats"] = lambda x: (f, d)        # the conv nets are out of scope
+        bev, dd = lss.get_voxels(None, rots.to(DEV), trans.to(DEV))
+        assert dd is d and rel_to_max(bev.detach().permute(0, 2, 3, 4, 1).cpu().numpy(), want) <= TOL, fused
+        bev.backward(gout.to(DEV))
+        assert rel_to_max(d.grad.cpu().numpy(), gd) <= TOL and rel_to_max(f.grad.cpu().numpy(), gf) <= TOL, fused
+        pkg.plugin.unpatch_lss_class(cls)
+    # nothing in range: the reference's sequence returns None (and prints), the fused route an all-zero grid
+    pkg.plugin.patch_lss_class(cls, fused=False)
+    far = trans.to(DEV) + 1e4
+    lss.__dict__["get_cam_feats"] = lambda x: (feat.to(DEV), depth.to(DEV))
+    assert lss.get_voxels(None, rots.to(DEV), far)[0] is None
+    pkg.plugin.patch_lss_class(cls, fused=True)
+    assert float(lss.get_voxels(None, rots.to(DEV), far)[0].abs().max()) == 0.0
+    pkg.plugin.unpatch_lss_class(cls)
+    _cleanup(refimport)
+
+
+def test_reference_op_module_unmodified_on_ctypes_ext(pkg, orc, refimport):
+    """The reference's own ops/bev_pool_v2/bev_pool.py — QuickCumsumCuda (:11-83), bev_pool_v2 (:86-92), TRTBEVPoolv2
+    (:95-142) and its known-answer test (:145-176) — executed unmodified with `bev_pool_v2_ext` resolved to this
+    package's binding of the C ABI."""
+    _cleanup(refimport)
+    op = refimport.import_reference_op(ext=pkg.plugin.install_ext())
+    assert op.bev_pool_v2_ext is pkg.bev_pool_v2_ext and op.QuickCumsumCuda is not pkg.QuickCumsumCuda
+    op.test_bev_pool_v2()                                        # the reference's KAT, its own asserts
+    cfg = pkg.synthetic.CONFIGS["bevdet_r50_b8"]
+    B = 2
+    view = pkg.LSSViewTransform.from_config(cfg)
+    rots, trans = pkg.synthetic.camera_ring(B, cfg.n_cams, cfg.final_dim, seed=0)
+    coor = orc.get_geometry(view.frustum.numpy(), rots.numpy(), trans.numpy())
+    rb, rd, rf, st, ln = orc.prepare_v2(coor, view.dx.numpy(), view.bx.numpy(), view.nx.numpy())
+    depth, feat, gout = pkg.synthetic.pool_inputs(cfg, batch=B, seed=0)
+    X, Y, Z = (int(v) for v in view.nx)
+    C = cfg.channels
+    feat_cl = feat.permute(0, 1, 3, 4, 2).contiguous()
+    shape = (B, view.nx[2], view.nx[1], view.nx[0], C)            # 0-dim LongTensors, as the reference passes them
+    same = orc.bev_pool_v2_forward(depth.numpy(), feat_cl.numpy(), rd, rf, rb, (B, Z, Y, X, C), st, ln)
+    exact = orc.bev_pool_v2_forward(depth.numpy(), feat_cl.numpy(), rd, rf, rb, (B, Z, Y, X, C), st, ln, exact=True)
+    gd, gf = orc.bev_pool_v2_backward(gout.permute(0, 2, 3, 4, 1).contiguous().numpy(), depth.numpy(), feat_cl.numpy(),
+                                      rd, rf, rb, exact=True)
+    d, f = depth.to(DEV).requires_grad_(), feat_cl.to(DEV).requires_grad_()
+    t = [torch.from_numpy(a).to(DEV) for a in (rd, rf, rb, st, ln)]
+    bev = op.bev_pool_v2(d, f, t[0], t[1], t[2], shape, t[3], t[4])
+    assert bev.shape == (B, C, Z, Y, X) and bev.is_contiguous()
+    assert np.array_equal(bev.detach().permute(0, 2, 3, 4, 1).cpu().numpy(), same)     # reference order + FMA: bit-identical
+    assert rel_to_max(bev.detach().permute(0, 2, 3, 4, 1).cpu().numpy(), exact) <= TOL
+    bev.backward(gout.to(DEV))                                    # the reference's own argsort / where regrouping
+    assert rel_to_max(d.grad.cpu().numpy(), gd) <= TOL and rel_to_max(f.grad.cpu().numpy(), gf) <= TOL
+    trt = op.TRTBEVPoolv2.apply(d.detach()[0], f.detach()[0], *_first_frame_ranks(orc, coor, view), Y, X)
+    assert trt.shape == (1, Y, X, C) and rel_to_max(trt.cpu().numpy()[0], exact[0, 0]) <= TOL
+    # loud errors where the reference has none
+    with pytest.raises(ValueError):
+        pkg.bev_pool_v2_ext.bev_pool_v2_forward(d.detach().cpu(), f.detach(), torch.zeros(shape, device=DEV), *t)
+    _cleanup(refimport)
+
+
+def _first_frame_ranks(orc, coor, view):
+    rb, rd, rf, st, ln = orc.prepare_v2(coor[:1], view.dx.numpy(), view.bx.numpy(), view.nx.numpy())
+    return [torch.from_numpy(a).to(DEV) for a in (rd, rf, rb, st, ln)]

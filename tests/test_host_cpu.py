@@ -199,3 +199,46 @@ def test_cross_modal_state_dict_keys_match_reference_construction(pkg):
                                                     sync.reduce_mixBEV.bn.running_var, sync.reduce_mixBEV.bn.weight,
                                                     sync.reduce_mixBEV.bn.bias, False, 0.0, sync.reduce_mixBEV.bn.eps))
     assert torch.allclose(sync.reduce_mixBEV.eval()(x), ref)
+
+
+def test_patch_real_reference_class_cpu(pkg):
+    """The UNMODIFIED reference LiftSplatShoot (imported from the staged files / the reference tree) is patched and
+    un-patched; on a CPU box the patched methods must refuse loudly (no CPU fallback), the cached fused view must not
+    show up in the module's state_dict, and the reference's own op module must import on the ctypes ext binding."""
+    sys.path.insert(0, ROOT)
+    from oracle import refimport as ri
+    if ri.ref_root() is None:
+        pytest.skip("reference Python files not staged")
+    pkg.plugin.install(force=True)
+    ref = ri.import_reference_lss("bevfusion")
+    assert ref.bev_pool_v2 is pkg.bev_pool_v2
+    lss = ri.make_reference_lss(ref, (64, 176), 8, (1.0, 60.0, 1.0), (-51.2, 51.2, 0.8), (-51.2, 51.2, 0.8), (-5.0, 3.0, 8.0))
+    keys = sorted(lss.state_dict())
+    orig = ref.LiftSplatShoot.get_voxels
+    pkg.plugin.patch_lss_class(ref.LiftSplatShoot)
+    assert ref.LiftSplatShoot.get_voxels is not orig
+    view = pkg.plugin.fused_view_of(lss)
+    assert view.frustum is lss.frustum and (view.D, view.fH, view.fW) == (59, 8, 22) and view.nx.tolist() == [128, 128, 1]
+    assert pkg.plugin.fused_view_of(lss) is view and sorted(lss.state_dict()) == keys and list(view.state_dict()) == []
+    lss.nx = lss.nx.clone()                                  # re-assigned constants invalidate the cached view
+    assert pkg.plugin.fused_view_of(lss) is not view
+    rots, trans = pkg.synthetic.camera_ring(1, 6, (64, 176), seed=0)
+    with pytest.raises(ValueError, match="CUDA"):
+        lss.get_geometry(rots, trans)
+    with pytest.raises(ValueError, match="CUDA"):
+        lss.get_voxels(torch.zeros(1, 6, 8, 8, 22), rots, trans)
+    # non-default transforms still reach the reference's own implementation (CPU torch ops)
+    coor = lss.get_geometry(rots, trans, post_rots=torch.eye(3).expand(1, 6, 3, 3), post_trans=torch.zeros(1, 6, 3))
+    assert coor.shape == (1, 6, 59, 8, 22, 3)
+    pkg.plugin.patch_lss_class(ref.LiftSplatShoot, fused=False)
+    assert ref.LiftSplatShoot.get_voxels is orig
+    pkg.plugin.unpatch_lss_class(ref.LiftSplatShoot)
+    assert ref.LiftSplatShoot.get_voxels is orig and not hasattr(ref.LiftSplatShoot, "_bevpool_b200_orig_prepare")
+    op = ri.import_reference_op(ext=pkg.plugin.install_ext())
+    assert op.bev_pool_v2_ext is pkg.bev_pool_v2_ext and op.__all__ == ['bev_pool_v2', 'TRTBEVPoolv2']
+    with pytest.raises(ValueError, match="CUDA"):
+        op.bev_pool_v2(torch.rand(1, 1, 2, 2, 2), torch.ones(1, 1, 2, 2, 2), torch.zeros(4).int(), torch.zeros(4).int(),
+                       torch.zeros(4).int(), (1, 1, 2, 2, 2), torch.zeros(1).int(), torch.ones(1).int())
+    for name in list(sys.modules):
+        if name.startswith("projects.mmdet3d_plugin"):
+            del sys.modules[name]
