@@ -106,11 +106,24 @@ def test_unmodified_reference_lss_with_patched_methods(pkg, orc, refimport, case
             o = np.lexsort((ranks_ref[1].cpu().numpy(), ranks_ref[0].cpu().numpy()))
             assert np.array_equal(ranks_ref[1].cpu().numpy()[o], ranks[1])
         x = x_in.clone().requires_grad_()
+        seen = {}
+
+        def cam_feats(xx, _orig=ref.LiftSplatShoot.get_cam_feats):      # the reference's own method; keep the grads
+            f, d = _orig(lss, xx)
+            f.retain_grad(), d.retain_grad()
+            seen["f"], seen["d"] = f, d
+            return f, d
+        lss.__dict__["get_cam_feats"] = cam_feats
         bev, depth = lss.get_voxels(x, rots.to(DEV), trans.to(DEV))
+        del lss.__dict__["get_cam_feats"]
         assert bev.shape == (B, 8, Z, Y, X) and depth.shape == (B, N, lss.D, lss.fH, lss.fW)
         assert rel_to_max(bev.detach().permute(0, 2, 3, 4, 1).cpu().numpy(), want) <= TOL, fused
         bev.backward(gout)
-        assert rel_to_max(x.grad.cpu().numpy(), x_chk.grad.cpu().numpy()) <= TOL, fused
+        # the pooling's own gradients at the 1e-5 bar; the module-input gradient additionally passes the 1x1 depthnet
+        # convolution, which cuDNN runs in TF32 by default (10-bit mantissa): compared at 1e-3
+        assert rel_to_max(seen["d"].grad.cpu().numpy(), gd) <= TOL, fused
+        assert rel_to_max(seen["f"].grad.cpu().numpy(), gf) <= TOL, fused
+        assert rel_to_max(x.grad.cpu().numpy(), x_chk.grad.cpu().numpy()) <= 1e-3, fused
         assert lss.s2c(bev).shape == (B, Z * 8, Y, X)
         assert sorted(lss.state_dict()) == keys_before            # nothing was registered on the reference module
         pkg.plugin.unpatch_lss_class(ref.LiftSplatShoot)
