@@ -15,6 +15,7 @@ step, bev_pool.py:47-68) and otherwise regroups on the device with a radix sort.
 Errors are loud: wrong device/dtype/shape raise ValueError, a failing kernel raises
 BevPoolError; nothing falls back to PyTorch ops or the CPU.
 """
+import os
 import weakref
 
 import torch
@@ -217,6 +218,15 @@ def _backward_general(out_grad_cl, depth, feat, rd, rf, rb):
     return depth_grad, feat_grad
 
 
+def _column_hint(Z):
+    """Which sort-free backward kernel to prefer: the column kernels pay when the pixels of an image column share
+    voxels (always for Z == 1). BEVPOOL_BWD_KERNEL=joint|block overrides (measurement / tests only)."""
+    env = os.environ.get("BEVPOOL_BWD_KERNEL")
+    if env in ("joint", "block"):
+        return 1 if env == "joint" else 0
+    return 1 if Z == 1 else 0
+
+
 def _backward_dense(out_grad_cl, depth, feat, plan, column_hint):
     lib = _lib.load()
     depth_grad = torch.empty_like(depth)
@@ -291,7 +301,7 @@ class _BevPoolV2Fused(torch.autograd.Function):
         og_cl = out_grad.new_empty((B, Z, Y, X, C))
         _launch_transpose(out_grad, og_cl, B, C, Z * Y * X, to_channels_last=True)
         if ctx.plan is not None and C % 4 == 0:
-            depth_grad, feat_grad = _backward_dense(og_cl, depth, feat, ctx.plan, column_hint=(Z == 1))
+            depth_grad, feat_grad = _backward_dense(og_cl, depth, feat, ctx.plan, column_hint=_column_hint(Z))
         else:
             depth_grad, feat_grad = _backward_general(og_cl, depth, feat, rd, rf, rb)
         return depth_grad.to(ctx.in_dtypes[0]), feat_grad.to(ctx.in_dtypes[1]), None, None, None, None, None, None

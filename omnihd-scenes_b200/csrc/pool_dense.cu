@@ -1319,6 +1319,9 @@ static int backward_block_t(const void* og, void* dg, void* fg, const void* dept
   return launch_status();
 }
 
+int backward_column(const void* og, void* dg, void* fg, const void* depth, const void* feat, const int* point_rank,
+                    int bn, int d, int h, int w, int c, int feat_grad_nchw, int dtype, cudaStream_t st, bool* handled);   // pool_column.cu
+
 }  // namespace bevpool
 
 using namespace bevpool;
@@ -1430,6 +1433,17 @@ extern "C" int bevpool_v2_backward_dense(const void* out_grad, void* depth_grad,
   if (dtype != BEVPOOL_F32 && dtype != BEVPOOL_BF16) return BEVPOOL_ERR_BAD_ARG;
   if (column_hint) {
     bool handled = false;
+    // column-GEMM kernel (pool_column.cu); BEVPOOL_BWD_COLUMN=0 keeps the round-1 joint kernel (A/B measurement only)
+    static int use_column = -1;
+    if (use_column < 0) {
+      const char* e = getenv("BEVPOOL_BWD_COLUMN");
+      use_column = !(e && e[0] == '0');
+    }
+    if (use_column) {
+      const int rc = backward_column(out_grad, depth_grad, feat_grad, depth, feat, point_rank, bn, d, h, w, c,
+                                     prm.feat_grad_nchw, dtype, st, &handled);
+      if (handled) return rc;
+    }
     const int rc = dtype == BEVPOOL_F32
                        ? backward_joint_t<float>(out_grad, depth_grad, feat_grad, depth, feat, point_rank, prm, st, &handled)
                        : backward_joint_t<__nv_bfloat16>(out_grad, depth_grad, feat_grad, depth, feat, point_rank, prm, st,

@@ -59,13 +59,16 @@ CONFIGS = {
 }
 
 
-def camera_ring(batch: int, n_cams: int, final_dim, seed: int = 0):
+def camera_ring(batch: int, n_cams: int, final_dim, seed: int = 0, roll: float = 0.0, pitch: float = 0.0):
     """rots [B,N,3,3], trans [B,N,3] fp32 = inverse(lidar2img)[:3,:3], [:3,3].
 
     Ring geometry per SURVEY.md §8(d): yaw_i = 2*pi*i/N + (u-0.5)*0.05 with u drawn
     in (b, i) order; cam->lidar columns [right | down | fwd]; pinhole K with
     f = 0.6*W. The inverse is taken per matrix in fp32 exactly as
     bevf_faster_rcnn.py:119-121 does (`torch.Tensor(mat).inverse()`).
+    roll / pitch (radians, default 0 = the SURVEY ring, bit-identical to before): every camera is additionally
+    rotated about its optical axis / its right axis, so the pixels of one image column no longer share a voxel
+    at a given depth (real calibrations; exercises the mixed-bin paths of the column kernels).
     """
     H, W = final_dim
     g = torch.Generator().manual_seed(seed)
@@ -86,6 +89,11 @@ def camera_ring(batch: int, n_cams: int, final_dim, seed: int = 0):
             cam2lidar[:3, 1] = torch.tensor([0.0, 0.0, -1.0], dtype=torch.float64)  # down
             cam2lidar[:3, 2] = torch.tensor([c, s, 0.0], dtype=torch.float64)    # fwd
             cam2lidar[:3, 3] = torch.tensor([0.5 * c, 0.5 * s, 1.5], dtype=torch.float64)
+            if roll != 0.0 or pitch != 0.0:
+                cr, sr, cp, sp = math.cos(roll), math.sin(roll), math.cos(pitch), math.sin(pitch)
+                rz = torch.tensor([[cr, -sr, 0.0], [sr, cr, 0.0], [0.0, 0.0, 1.0]], dtype=torch.float64)
+                rx = torch.tensor([[1.0, 0.0, 0.0], [0.0, cp, -sp], [0.0, sp, cp]], dtype=torch.float64)
+                cam2lidar[:3, :3] = cam2lidar[:3, :3] @ rz @ rx
             lidar2img = (K @ torch.linalg.inv(cam2lidar)).numpy()
             mat = torch.Tensor(lidar2img)          # fp32, as the reference does
             inv = mat.inverse()

@@ -21,7 +21,7 @@ from torch import nn
 
 from . import _lib
 from .bev_pool import bev_pool_v2, register_plan, _ptr, _stream, _launch_forward_dense, _launch_transpose, \
-    _launch_voxel_table, _dtype_code
+    _launch_voxel_table, _dtype_code, _column_hint
 
 
 # ----------------------------------------------------------------------------- constants
@@ -206,15 +206,6 @@ class _Fork:
         if len(self.streams) > 1 or self.streams[0] is not self.cur:
             for st in self.streams:
                 self.cur.wait_stream(st)
-
-
-def _column_hint(Z):
-    """Which sort-free backward kernel to prefer: the joint-column walk pays when vertically adjacent pixels
-    share voxels (always for Z == 1). BEVPOOL_BWD_KERNEL=joint|block overrides (measurement only)."""
-    env = os.environ.get("BEVPOOL_BWD_KERNEL")
-    if env in ("joint", "block"):
-        return 1 if env == "joint" else 0
-    return 1 if Z == 1 else 0
 
 
 class _FusedViewPool(torch.autograd.Function):

@@ -34,10 +34,10 @@ def canon_ties(rb, rd, rf):
     return rb[order], rd[order], rf[order]
 
 
-def synth_pool_case(pkg, orc, cfg, B, seed=0):
+def synth_pool_case(pkg, orc, cfg, B, seed=0, roll=0.0, pitch=0.0):
     """Full pipeline inputs on the host + oracle prepare outputs."""
     view = pkg.LSSViewTransform.from_config(cfg)
-    rots, trans = pkg.synthetic.camera_ring(B, cfg.n_cams, cfg.final_dim, seed=seed)
+    rots, trans = pkg.synthetic.camera_ring(B, cfg.n_cams, cfg.final_dim, seed=seed, roll=roll, pitch=pitch)
     coor = orc.get_geometry(view.frustum.numpy(), rots.numpy(), trans.numpy())
     ranks = orc.prepare_v2(coor, view.dx.numpy(), view.bx.numpy(), view.nx.numpy())
     depth, feat, gout = pkg.synthetic.pool_inputs(cfg, batch=B, seed=seed)
@@ -341,11 +341,11 @@ def test_backward_general_path_vs_oracle(pkg, orc, case):
         assert rel_to_max(f.grad.cpu().numpy(), gf) <= TOL
 
 
-def _view_modes_vs_oracle(pkg, orc, cfg, B, dt, modes, seed=0):
+def _view_modes_vs_oracle(pkg, orc, cfg, B, dt, modes, seed=0, roll=0.0, pitch=0.0):
     """Run the public view-transform paths in dtype `dt` and compare with the float64 oracle fed the SAME
     (dt-rounded) inputs. fp32: 1e-5 of max (north_star); bf16: 2^-8 of max (one output rounding,
     fp32 accumulation inside)."""
-    view, rots, trans, coor, (rb, rd, rf, st, ln), depth, feat, gout = synth_pool_case(pkg, orc, cfg, B, seed)
+    view, rots, trans, coor, (rb, rd, rf, st, ln), depth, feat, gout = synth_pool_case(pkg, orc, cfg, B, seed, roll, pitch)
     tol = TOL if dt == torch.float32 else TOL_BF16
     depth, feat, gout = (t.to(dt) for t in (depth, feat, gout))
     dq, fq, gq = depth.float(), feat.float(), gout.float()           # what the kernels actually read
@@ -391,6 +391,34 @@ def test_view_transform_fwd_bwd_vs_oracle(pkg, orc, cfg_name, B):
     cfg = pkg.synthetic.CONFIGS[cfg_name]
     dt = torch.bfloat16 if cfg.dtype == "bf16" else torch.float32
     _view_modes_vs_oracle(pkg, orc, cfg, B, dt, ALL_MODES)
+
+
+@pytest.mark.parametrize("cfg_name,dt,roll,pitch", [("bevdet_r50_b8", torch.float32, 0.08, 0.03),
+                                                     ("bevdet_r50_b8", torch.float32, 0.6, 0.0),
+                                                     ("bevdepth_hires_b16", torch.bfloat16, 0.05, -0.04)])
+def test_rolled_cameras_mixed_column_bins(pkg, orc, cfg_name, dt, roll, pitch):
+    """Cameras with roll / pitch (real calibrations): the 16 pixels of an image column no longer share one voxel per
+    depth bin, so the column kernels' mixed-bin slow paths carry real work (the SURVEY ring never reaches them).
+    Every public path against the oracle."""
+    cfg = pkg.synthetic.CONFIGS[cfg_name]
+    view, rots, trans, coor, ranks, *_ = synth_pool_case(pkg, orc, cfg, 1, 6, roll, pitch)
+    rank = np.asarray(orc.voxel_rank(coor, view.dx.numpy(), view.bx.numpy(), view.nx.numpy())).reshape(coor.shape[1:5])   # [N, D, H, W]
+    kept = rank >= 0
+    lead = np.where(kept, rank, -1).max(axis=2, keepdims=True)
+    assert ((rank != lead) & kept).sum() > 0.02 * kept.sum()          # a real share of the points sits in mixed bins
+    _view_modes_vs_oracle(pkg, orc, cfg, 2, dt, ALL_MODES, seed=6, roll=roll, pitch=pitch)
+
+
+@pytest.mark.parametrize("cfg_name,B", [("occ_200x200x16_b64", 2), ("rcfusion_omnihd_small", 2)])
+def test_column_backward_forced_on_z16_grids(pkg, orc, cfg_name, B, monkeypatch):
+    """BEVPOOL_BWD_KERNEL=joint forces the column-GEMM backward onto Z = 16 grids, where almost every (column, bin)
+    holds several voxels: its slow path (one extra item per additional voxel) must give the same gradients as the
+    block kernels that are the default there."""
+    import dataclasses
+    C = pkg.synthetic.CONFIGS
+    cfg = C[cfg_name] if cfg_name in C else dataclasses.replace(C["rcfusion_omnihd_b32"], final_dim=(136, 240))
+    monkeypatch.setenv("BEVPOOL_BWD_KERNEL", "joint")
+    _view_modes_vs_oracle(pkg, orc, cfg, B, torch.float32, ("fused", "api"), seed=2)
 
 
 def _bf16_cases(pkg):
