@@ -383,3 +383,33 @@ def _scatter_dense(shape, g, x):
     flat = ((g[:, 3] * Z + g[:, 2]) * Y + g[:, 1]) * X + g[:, 0]              # voxel id without channel
     out = torch.zeros((B * Z * Y * X, C), dtype=x.dtype).index_copy(0, flat, x)
     return out.view(B, Z, Y, X, C).permute(0, 4, 1, 2, 3).contiguous()
+
+
+def cpu_reference_class_step(ref, lss, rots, trans, depth, feat, out_grad):
+    """The same CPU step with the REFERENCE'S OWN code wherever it still exists (bench.py `kind: "reference"`):
+    `lss` is an unmodified reference LiftSplatShoot (oracle/refimport.py) — its get_geometry (:229-258) and its
+    QuickCumsum autograd Function (:96-122) run as they are; the voxelise / mask / rank / argsort glue and the dense
+    scatter are restated from upstream LSS `voxel_pooling` (the reference deleted that method and kept only the cumsum
+    core). torch CPU tensors; returns (bev, depth_grad, feat_grad)."""
+    import torch
+    B, N = trans.shape[:2]
+    D, H, W, _ = lss.frustum.shape
+    C = feat.shape[2]
+    dx, bx, nx = lss.dx, lss.bx, lss.nx
+    depth = depth.detach().requires_grad_()
+    feat = feat.detach().requires_grad_()
+    with torch.no_grad():
+        coor = lss.get_geometry(rots, trans)
+    g = ((coor - (bx - dx / 2.)) / dx).long().view(-1, 3)
+    bidx = torch.arange(B).view(B, 1).expand(B, N * D * H * W).reshape(-1, 1)
+    g = torch.cat((g, bidx), 1)
+    kept = (g[:, 0] >= 0) & (g[:, 0] < nx[0]) & (g[:, 1] >= 0) & (g[:, 1] < nx[1]) & (g[:, 2] >= 0) & (g[:, 2] < nx[2])
+    x = (depth.unsqueeze(-1) * feat.permute(0, 1, 3, 4, 2).unsqueeze(2)).reshape(-1, C)
+    x, g = x[kept], g[kept]
+    ranks = g[:, 3] * (nx[2] * nx[1] * nx[0]) + g[:, 2] * (nx[1] * nx[0]) + g[:, 1] * nx[0] + g[:, 0]
+    order = ranks.argsort()
+    x, g, ranks = x[order], g[order], ranks[order]
+    x, g = ref.QuickCumsum.apply(x, g, ranks)
+    final = _scatter_dense((B, C, int(nx[2]), int(nx[1]), int(nx[0])), g, x)
+    final.backward(out_grad)
+    return final.detach(), depth.grad, feat.grad
