@@ -214,3 +214,57 @@ def test_reference_op_module_unmodified_on_ctypes_ext(pkg, orc, refimport):
 def _first_frame_ranks(orc, coor, view):
     rb, rd, rf, st, ln = orc.prepare_v2(coor[:1], view.dx.numpy(), view.bx.numpy(), view.nx.numpy())
     return [torch.from_numpy(a).to(DEV) for a in (rd, rf, rb, st, ln)]
+
+
+def test_trt_bev_pool_v2_onnx_symbolic(pkg, orc):
+    """TRTBEVPoolv2.symbolic (ops/bev_pool_v2/bev_pool.py:98-119): tracing a module that calls TRTBEVPoolv2.apply through
+    torch's ONNX graph builder must emit ONE `mmdeploy::bev_pool_v2` node with the seven tensor inputs and the integer
+    attributes out_height / out_width — the node mmdeploy's TensorRT plugin consumes. (The `onnx` package is not in this
+    image, so the graph is inspected before serialisation; torch.onnx.export proper fails only at that last step.)"""
+    try:
+        from torch.onnx._internal.torchscript_exporter import utils as U
+        from torch.onnx._internal.torchscript_exporter._globals import GLOBALS
+    except ImportError:
+        pytest.skip("torch's TorchScript ONNX exporter internals are not importable in this build")
+    cfg = pkg.synthetic.ViewConfig("onnx", (64, 176), 16, (1.0, 60.0, 1.0), (-51.2, 51.2, 0.8), (-51.2, 51.2, 0.8), (-5.0, 3.0, 8.0),
+                                   16, 1)
+    view = pkg.LSSViewTransform.from_config(cfg)
+    rots, trans = pkg.synthetic.camera_ring(1, cfg.n_cams, cfg.final_dim, seed=1)
+    coor = orc.get_geometry(view.frustum.numpy(), rots.numpy(), trans.numpy())
+    rb, rd, rf, st, ln = orc.prepare_v2(coor, view.dx.numpy(), view.bx.numpy(), view.nx.numpy())
+    depth, feat, _ = pkg.synthetic.pool_inputs(cfg, seed=1)
+    X, Y, Z = (int(v) for v in view.nx)
+    t = [torch.from_numpy(a).to(DEV) for a in (rd, rf, rb, st, ln)]
+    d, f = depth[0].to(DEV), feat[0].permute(0, 2, 3, 1).contiguous().to(DEV)
+
+    class Pool(torch.nn.Module):
+        def forward(self, depth, feat, rd, rf, rb, st, ln):
+            return pkg.TRTBEVPoolv2.apply(depth, feat, rd, rf, rb, st, ln, Y, X)
+    want = orc.bev_pool_v2_forward(depth.numpy(), f.cpu().numpy()[None], rd, rf, rb, (1, Z, Y, X, cfg.channels), st, ln, exact=True)
+    assert rel_to_max(Pool()(d, f, *t).cpu().numpy()[0], want[0, 0]) <= TOL
+    GLOBALS.export_onnx_opset_version = 13
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        graph, _, _ = U._model_to_graph(Pool(), (d, f, *t))
+    nodes = [n for n in graph.nodes() if n.kind() == "mmdeploy::bev_pool_v2"]
+    assert len(nodes) == 1
+    n = nodes[0]
+    assert len(list(n.inputs())) == 7 and sorted(n.attributeNames()) == ["out_height", "out_width"]
+    assert n.i("out_height") == Y and n.i("out_width") == X
+    # the reference's own symbolic emits the identical node (same name, attributes and input order)
+    sys.path.insert(0, ROOT)
+    from oracle import refimport as ri
+    if ri.ref_root() is not None:
+        op = ri.import_reference_op(ext=pkg.plugin.install_ext())
+
+        class RefPool(torch.nn.Module):
+            def forward(self, depth, feat, rd, rf, rb, st, ln):
+                return op.TRTBEVPoolv2.apply(depth, feat, rd, rf, rb, st, ln, Y, X)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            g2, _, _ = U._model_to_graph(RefPool(), (d, f, *t))
+        n2 = [m for m in g2.nodes() if m.kind() == "mmdeploy::bev_pool_v2"]
+        assert len(n2) == 1 and sorted(n2[0].attributeNames()) == sorted(n.attributeNames())
+        assert n2[0].i("out_height") == Y and n2[0].i("out_width") == X and len(list(n2[0].inputs())) == 7
+        _cleanup(ri)
