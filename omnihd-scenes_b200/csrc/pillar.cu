@@ -39,16 +39,37 @@ pillar_canvas_kernel(const T* __restrict__ feats, const int* __restrict__ pillar
   const int ncol = (int)min((int64_t)kPcCols, cells - c0);
   if (threadIdx.x < kPcCols) s_idx[threadIdx.x] = threadIdx.x < ncol ? __ldg(pillar_index + bi * cells + c0 + threadIdx.x) : -1;
   __syncthreads();
-  for (int i = threadIdx.x; i < ncol * c; i += 256) {
-    const int col = i / c, ch = i - col * c;
-    const int p = s_idx[col];
-    t[ch * (kPcCols + 1) + col] = p >= 0 ? Vec4<T>::load1(feats, (int64_t)p * c + ch) : 0.f;
+  const bool vec_in = (c & 3) == 0 && (((uintptr_t)feats) & 15) == 0;
+  if (vec_in) {   // pillar rows as 128-bit pieces (a row is c*e contiguous bytes)
+    const int c4 = c >> 2;
+    for (int i = threadIdx.x; i < ncol * c4; i += 256) {
+      const int col = i / c4, q = i - col * c4;
+      const int p = s_idx[col];
+      const float4 v = p >= 0 ? Vec4<T>::load_stream(feats, (int64_t)p * c + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float* o = t + (4 * q) * (kPcCols + 1) + col;
+      o[0] = v.x; o[kPcCols + 1] = v.y; o[2 * (kPcCols + 1)] = v.z; o[3 * (kPcCols + 1)] = v.w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < ncol * c; i += 256) {
+      const int col = i / c, ch = i - col * c;
+      const int p = s_idx[col];
+      t[ch * (kPcCols + 1) + col] = p >= 0 ? Vec4<T>::load1(feats, (int64_t)p * c + ch) : 0.f;
+    }
   }
   __syncthreads();
   T* d = canvas + (bi * c) * cells + c0;
-  for (int i = threadIdx.x; i < c * kPcCols; i += 256) {
-    const int ch = i / kPcCols, q = i % kPcCols;
-    if (q < ncol) Vec4<T>::store1s(d, (int64_t)ch * cells + q, t[ch * (kPcCols + 1) + q]);
+  const bool vec_out = ncol == kPcCols && (cells & 3) == 0 && (((uintptr_t)canvas) & 15) == 0;
+  if (vec_out) {   // 4 consecutive cells of one channel per store: 128-bit (fp32) / 64-bit (bf16)
+    for (int i = threadIdx.x; i < c * (kPcCols / 4); i += 256) {
+      const int ch = i / (kPcCols / 4), q = i % (kPcCols / 4);
+      const float* pp = t + ch * (kPcCols + 1) + 4 * q;
+      Vec4<T>::store(d, (int64_t)ch * cells + 4 * q, make_float4(pp[0], pp[1], pp[2], pp[3]));
+    }
+  } else {
+    for (int i = threadIdx.x; i < c * kPcCols; i += 256) {
+      const int ch = i / kPcCols, q = i % kPcCols;
+      if (q < ncol) Vec4<T>::store1s(d, (int64_t)ch * cells + q, t[ch * (kPcCols + 1) + q]);
+    }
   }
 }
 
