@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/bevpool_b200.h"
 
@@ -246,11 +247,26 @@ __device__ __forceinline__ void cam_point(const float* __restrict__ frustum, con
   z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cam[6], px), __fmul_rn(cam[7], py)), __fmul_rn(cam[8], pz)), cam[11]);
 }
 
-// inv > 0: dx is a power of two and inv = 1/dx exactly, so the IEEE divide is a multiply (bit-identical: both are the
-// correctly rounded value of the same real number); inv == 0: true divide.
+// Voxel index of one coordinate: trunc((c - lo) / dx) with the reference's IEEE fp32 subtract and DIVIDE, bit for bit.
+//   inv > 0 : dx is a power of two and inv = 1/dx exactly: the divide IS a multiply (both are the correctly rounded
+//             value of the same real number);
+//   inv < 0 : -inv = fl(1/dx). q' = fl(t * fl(1/dx)) is within 2^-23 |q| of the true quotient and so is the IEEE
+//             quotient q = fl(t / dx): unless q' lies within a guard band of 2^-21 |q'| of an integer, no integer
+//             separates q from q', so trunc(q) == trunc(q') and both compare alike with the integers -1 and n — the
+//             divide (about 10 instructions, three per point) is skipped. Inside the band (about 1 point in 10^4),
+//             or for NaN, the true divide decides. tests/test_gpu_parity.py::test_voxel_boundaries_bit_exact pins it;
+//   inv == 0: always divide.
 __device__ __forceinline__ bool voxel_index(float c, float lo, float dx, float inv, int n, int& v) {
   const float t = __fsub_rn(c, lo);
-  const float q = inv > 0.f ? __fmul_rn(t, inv) : __fdiv_rn(t, dx);
+  float q;
+  if (inv > 0.f) {
+    q = __fmul_rn(t, inv);
+  } else if (inv < 0.f) {
+    q = __fmul_rn(t, -inv);
+    if (!(fabsf(q - rintf(q)) > fabsf(q) * 4.76837158203125e-7f)) q = __fdiv_rn(t, dx);   // 2^-21; NaN lands here too
+  } else {
+    q = __fdiv_rn(t, dx);
+  }
   // .long() truncates toward zero, so (-1, 0) lands in voxel 0 and is KEPT; trunc(q) in [0, n) <=> -1 < q < n
   // (n < 2^24 is exact in fp32). NaN / inf fail both comparisons (the CPU's INT64_MIN is dropped too).
   if (!(q > -1.0f && q < (float)n)) return false;
@@ -258,10 +274,13 @@ __device__ __forceinline__ bool voxel_index(float c, float lo, float dx, float i
   return true;
 }
 
-// 1/dx if dx is a positive power of two (then exact), else 0
+// see voxel_index: 1/dx if dx is a positive power of two (exact), -fl(1/dx) for any other positive finite dx, else 0
 inline float exact_reciprocal_or_zero(float dx) {
   int e = 0;
-  return (dx > 0.f && frexpf(dx, &e) == 0.5f) ? 1.0f / dx : 0.f;
+  if (!(dx > 0.f) || !isfinite(dx)) return 0.f;
+  if (frexpf(dx, &e) == 0.5f) return 1.0f / dx;
+  const float r = 1.0f / dx;
+  return (isfinite(r) && r > 0.f && getenv("BEVPOOL_EXACT_DIVIDE") == nullptr) ? -r : 0.f;
 }
 
 }  // namespace bevpool

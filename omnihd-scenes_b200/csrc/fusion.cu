@@ -54,29 +54,19 @@ channel_avg_max_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, int* __
     mx[k] = 0.f;
     am[k] = -1;
   }
-  // U channel planes are requested before the first is consumed (the max / argmax bookkeeping is branchy, so the
-  // compiler would not hoist the loads by itself): U x V x 4 bytes in flight per thread
-  constexpr int U = 6;
-  for (int ch0 = warp; ch0 < c; ch0 += kFuWarps * U) {
-    float v[U][V];
+#pragma unroll 4
+  for (int ch = warp; ch < c; ch += kFuWarps) {
+    float v[V];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
+    for (int k = 0; k < V; ++k) v[k] = 0.f;
+    if (in) PixIO<T, V>::load(xp + (int64_t)ch * hw, v);
 #pragma unroll
-      for (int k = 0; k < V; ++k) v[u][k] = 0.f;
-      if (in && ch0 + u * kFuWarps < c) PixIO<T, V>::load(xp + (int64_t)(ch0 + u * kFuWarps) * hw, v[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int ch = ch0 + u * kFuWarps;
-      if (ch >= c) break;
-#pragma unroll
-      for (int k = 0; k < V; ++k) {
-        sum[k] += v[u][k];
-        // the first maximum wins; the first NaN wins and sticks (torch.max semantics)
-        if (am[k] < 0 || v[u][k] > mx[k] || (v[u][k] != v[u][k] && mx[k] == mx[k])) {
-          mx[k] = v[u][k];
-          am[k] = ch;
-        }
+    for (int k = 0; k < V; ++k) {
+      sum[k] += v[k];
+      // the first maximum wins; the first NaN wins and sticks (torch.max semantics)
+      if (am[k] < 0 || v[k] > mx[k] || (v[k] != v[k] && mx[k] == mx[k])) {
+        mx[k] = v[k];
+        am[k] = ch;
       }
     }
   }

@@ -1022,7 +1022,10 @@ pool_bwd_joint_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
           cmax = max(cmax, code[u]);
           cmin = min(cmin, code[u]);
         }
-        if (cmax == -1) continue;   // group-uniform: the bins are empty (dropped points come in long runs)
+        // group-uniform: ALL bins of the pass are empty (dropped points come in long runs). Mixed bins carry codes
+        // <= -2, so the maximum alone does not tell (round 1 tested `cmax == -1` and skipped a mixed bin that shared its
+        // pass with an empty one: wrong gradients under camera roll; caught by test_rolled_cameras_mixed_column_bins)
+        if (cmax == -1 && cmin == -1) continue;
         if (cmin >= -1) {
           // no mixed column among the bins: straight-line code, no per-bin branches. Empty bins ride along with
           // g = 0 and weights 0 (their partials are discarded by the reducing lane below).

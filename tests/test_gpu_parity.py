@@ -115,6 +115,64 @@ def test_prepare_none_when_nothing_in_range(pkg):
                                         torch.from_numpy(g["nx"])) == (None,) * 5
 
 
+@pytest.mark.parametrize("step", [0.8, 0.512, 0.4, 0.3, 0.5, 1.7])
+def test_voxel_boundaries_bit_exact(pkg, orc, step):
+    """The voxel index is trunc((c - lo) / dx) with an IEEE divide (cam_stream_lss_bevpoolv2.py:317-318). The kernels
+    replace the divide by a multiply with fl(1/dx) outside a guard band around the integers (csrc/common.cuh
+    voxel_index): coordinates ON every voxel boundary and 1..3 ulps either side of it — where a reciprocal multiply
+    alone flips indices — must still give the reference's ranks bit for bit, from materialised coordinates and through
+    the fused geometry (identity camera, so the frustum values ARE the coordinates)."""
+    n = 200
+    lo_edge = np.float32(-0.5 * n * step)
+    dx = torch.tensor([step, step, 8.0])
+    bx = torch.tensor([float(lo_edge) + step / 2.0, float(lo_edge) + step / 2.0, -1.0])
+    nx = torch.tensor([n, n, 1])
+    lo32 = (bx - dx / 2.0).numpy()[0]
+    ks = np.arange(-2, n + 3, dtype=np.float64)
+    base = (np.float64(lo32) + ks * np.float64(np.float32(step))).astype(np.float32)
+    xs = [base]
+    for _ in range(3):
+        xs.append(np.nextafter(xs[-1], np.float32(np.inf)))
+    lo_side = base
+    for _ in range(3):
+        lo_side = np.nextafter(lo_side, np.float32(-np.inf))
+        xs.append(lo_side)
+    xs = np.concatenate(xs + [base + np.float32(step * 0.37)]).astype(np.float32)     # + generic interior points
+    W = xs.size
+    coor = np.zeros((1, 1, 2, 1, W, 3), np.float32)
+    coor[0, 0, 0, 0, :, 0] = xs                      # adversarial x, fixed y
+    coor[0, 0, 0, 0, :, 1] = np.float32(0.1)
+    coor[0, 0, 1, 0, :, 0] = np.float32(0.1)         # fixed x, adversarial y
+    coor[0, 0, 1, 0, :, 1] = xs
+    want = orc.prepare_v2(coor, dx.numpy(), bx.numpy(), nx.numpy())
+    got = pkg.voxel_pooling_prepare_v2(cu(coor), dx, bx, nx)
+    for a, b in zip(got, want):
+        assert np.array_equal(a.cpu().numpy(), b)
+    # a bare reciprocal multiply is NOT equivalent on these inputs (the test would be vacuous otherwise)
+    t = coor[..., 0] - lo32
+    assert np.any((t * np.float32(1.0 / np.float32(step))).astype(np.int64) != (t / np.float32(step)).astype(np.int64)) \
+        or step in (0.5,)
+    # fused geometry: rots = I, trans = 0, frustum = (x, y, 1) -> coor == frustum values
+    vt = pkg.view_transform
+
+    class V:
+        pass
+    v = V()
+    v.dx, v.bx, v.nx = dx, bx, nx
+    fr = np.zeros((2, 1, W, 3), np.float32)
+    fr[..., 2] = 1.0
+    fr[0, 0, :, 0], fr[0, 0, :, 1] = xs, np.float32(0.1)
+    fr[1, 0, :, 0], fr[1, 0, :, 1] = np.float32(0.1), xs
+    v.frustum = cu(fr)
+    C = 8
+    out = torch.empty((1, 1, n, n, C), device=DEV)
+    pr = vt._view_forward_scatter(torch.ones((1, 1, 2, 1, W), device=DEV), torch.ones((1, 1, 1, W, C), device=DEV), out, v,
+                                  torch.eye(3, device=DEV).view(1, 1, 3, 3), torch.zeros((1, 1, 3), device=DEV), 1, 1, 2, 1, W, C,
+                                  1, n, pkg._lib.LAYOUT_BZYXC)
+    rank = orc.voxel_rank(coor, dx.numpy(), bx.numpy(), nx.numpy()).reshape(-1)
+    assert np.array_equal(pr.point_rank.cpu().numpy().astype(np.int64), rank)
+
+
 def test_prepare_truncation_nan_inf(pkg, orc):
     dx = torch.tensor([1., 1., 1.])
     bx = torch.tensor([.5, .5, .5])
