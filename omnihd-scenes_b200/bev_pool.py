@@ -27,7 +27,9 @@ __all__ = ['bev_pool_v2', 'TRTBEVPoolv2']
 
 # ----------------------------------------------------------------------------- helpers
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    # raw handle of the current stream of the current device (torch.cuda.current_stream() builds a Stream object and
+    # costs ~4 us a call; this path is taken 6+ times per step)
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _ptr(t):

@@ -374,6 +374,7 @@ head_count_kernel(const int* __restrict__ keys, const int* __restrict__ vals, co
                   int* __restrict__ ranks_feat, int dhw, int hw,                                   // MODE 0
                   const int* __restrict__ src_rd, const int* __restrict__ src_rb, int* __restrict__ dst_rd,
                   int* __restrict__ dst_rb) {                                                      // MODE 1
+  pdl_wait();
   __shared__ uint32_t s_cnt;
   const int tid = threadIdx.x;
   if (tid == 0) s_cnt = 0;
@@ -410,6 +411,7 @@ head_count_kernel(const int* __restrict__ keys, const int* __restrict__ vals, co
 
 __global__ void __launch_bounds__(256)
 head_scan_kernel(uint32_t* __restrict__ tile_counts, int64_t n_tiles, int* __restrict__ n_heads_out) {
+  pdl_wait();
   __shared__ uint32_t scan_tmp[8];
   uint32_t carry = 0;
   for (int64_t t0 = 0; t0 < n_tiles; t0 += 256) {
@@ -426,6 +428,7 @@ head_scan_kernel(uint32_t* __restrict__ tile_counts, int64_t n_tiles, int* __res
 __global__ void __launch_bounds__(kHeadThreads)
 head_write_kernel(const int* __restrict__ keys, const int* __restrict__ n_dev, int64_t n_host, int rounds,
                   const uint32_t* __restrict__ tile_prefix, int* __restrict__ starts) {
+  pdl_wait();
   __shared__ uint32_t scan_tmp[8];
   const int tid = threadIdx.x;
   const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
@@ -451,6 +454,7 @@ head_write_kernel(const int* __restrict__ keys, const int* __restrict__ n_dev, i
 
 __global__ void interval_lengths_kernel(const int* __restrict__ starts, const int* __restrict__ n_heads_dev,
                                         const int* __restrict__ n_dev, int64_t n_host, int* __restrict__ lengths) {
+  pdl_wait();
   const int n_heads = *n_heads_dev;
   const int n = n_dev ? *n_dev : (int)n_host;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_heads; j += (int64_t)gridDim.x * blockDim.x)
@@ -628,19 +632,20 @@ extern "C" int bevpool_prepare_v2(const float* coor, const float* frustum, const
   run_passes(plan, w, point_rank, nullptr, p0, counts_dev, ranks_bev, ranks_depth, st);
 
   if (interval_starts || ranks_feat) {
-    head_count_kernel<0><<<(unsigned)plan.head_tiles, kHeadThreads, 0, st>>>(
-        ranks_bev, ranks_depth, counts_dev, p0, plan.head_rounds, w.head_counts, ranks_feat, gd.dhw, g->h * g->w,
-        nullptr, nullptr, nullptr, nullptr);
+    launch_pdl(head_count_kernel<0>, dim3((unsigned)plan.head_tiles), dim3(kHeadThreads), 0, st, (const int*)ranks_bev,
+               (const int*)ranks_depth, (const int*)counts_dev, (int64_t)p0, plan.head_rounds, w.head_counts, ranks_feat, gd.dhw,
+               g->h * g->w, (const int*)nullptr, (const int*)nullptr, (int*)nullptr, (int*)nullptr);
     count_launch();
   }
   if (interval_starts) {
-    head_scan_kernel<<<1, 256, 0, st>>>(w.head_counts, plan.head_tiles, counts_dev + 1);
-    head_write_kernel<<<(unsigned)plan.head_tiles, kHeadThreads, 0, st>>>(ranks_bev, counts_dev, p0, plan.head_rounds,
-                                                                         w.head_counts, interval_starts);
+    launch_pdl(head_scan_kernel, dim3(1), dim3(256), 0, st, w.head_counts, (int64_t)plan.head_tiles, counts_dev + 1);
+    launch_pdl(head_write_kernel, dim3((unsigned)plan.head_tiles), dim3(kHeadThreads), 0, st, (const int*)ranks_bev,
+               (const int*)counts_dev, (int64_t)p0, plan.head_rounds, (const uint32_t*)w.head_counts, interval_starts);
     int lb = (int)(((v < p0 ? v : p0) + 255) / 256);
     if (lb > kNumSMs * 8) lb = kNumSMs * 8;
     if (lb < 1) lb = 1;
-    interval_lengths_kernel<<<lb, 256, 0, st>>>(interval_starts, counts_dev + 1, counts_dev, p0, interval_lengths);
+    launch_pdl(interval_lengths_kernel, dim3(lb), dim3(256), 0, st, (const int*)interval_starts, (const int*)(counts_dev + 1),
+               (const int*)counts_dev, (int64_t)p0, interval_lengths);
     count_launch(3);
   }
   return launch_status();

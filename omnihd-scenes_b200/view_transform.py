@@ -60,7 +60,31 @@ def _check_f32_cuda(name, t, shape_tail=None):
         raise ValueError(f"{name} must end with shape {tuple(shape_tail)}, got {tuple(t.shape)}")
 
 
+_GRID_CACHE = {}
+
+
 def _grid_struct(B, N, D, H, W, dx, bx, nx):
+    """bevpool_grid_t for this call. The three constants are small CPU (sometimes CUDA) tensors that never change in
+    practice: the converted values are cached per tensor identity + version (a CUDA tensor would cost a sync each call)."""
+    key = None
+    if all(isinstance(t, torch.Tensor) for t in (dx, bx, nx)):
+        key = (id(dx), dx._version, id(bx), bx._version, id(nx), nx._version)
+        hit = _GRID_CACHE.get(key)
+        if hit is not None and hit[0]() is dx and hit[1]() is bx and hit[2]() is nx:
+            g = _lib.GridT()
+            g.b, g.n, g.d, g.h, g.w = B, N, D, H, W
+            g.nx[:], g.lo[:], g.dx[:] = hit[3], hit[4], hit[5]
+            return g
+    g = _grid_struct_uncached(B, N, D, H, W, dx, bx, nx)
+    if key is not None:
+        import weakref
+        if len(_GRID_CACHE) > 64:
+            _GRID_CACHE.clear()
+        _GRID_CACHE[key] = (weakref.ref(dx), weakref.ref(bx), weakref.ref(nx), list(g.nx), list(g.lo), list(g.dx))
+    return g
+
+
+def _grid_struct_uncached(B, N, D, H, W, dx, bx, nx):
     dx = torch.as_tensor(dx).detach().to("cpu", torch.float32)
     bx = torch.as_tensor(bx).detach().to("cpu", torch.float32)
     nx = torch.as_tensor(nx).detach().to("cpu", torch.int64)
