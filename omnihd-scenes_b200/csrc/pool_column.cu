@@ -168,14 +168,15 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int d_pad = (prm.d + 7) & ~7;
   const int CS = d_pad * kCgRows + 4;       // column stride of the [w][d][16] arrays: (4 w + h) mod 32 distinct per warp access
-  float* s_dg = reinterpret_cast<float*>(smem_raw);                                   // [8][CS] depth_grad of the tile
-  float* s_depth = s_dg + kCgW * CS;                                                 // [8][CS]
+  float* s_depth = reinterpret_cast<float*>(smem_raw);                                // [8][CS] lead-masked depth weights
   T* s_R = reinterpret_cast<T*>(s_depth + kCgW * CS);                                // [8 columns][stages][chunk][C]
   uint64_t* s_full = reinterpret_cast<uint64_t*>(s_R + kCgW * kCgStages * kCgChunk * C);   // [8][stages] rows have landed
   int* s_lead = reinterpret_cast<int*>(s_full + kCgW * kCgStages);                   // [8][d_pad] lead rank, -1 = empty bin
   int* s_items = s_lead + kCgW * d_pad;   // [8][d_pad]: per-bin summary (row mask | more << 16), later compacted in place to
                                           // the kept bins: bin | row mask << 8 | more << 24
   float* s_tile = s_depth;                // epilogue: [C][129] feat_grad transpose (over s_depth and the rings)
+  // depth_grad goes straight to global memory: zeros for dropped points while staging, one 4-byte store per kept point from
+  // the lane that holds its dot product (no shared-memory copy of the tile's gradients: half the footprint, D = 118 fits)
 
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const int hl = lane >> 3, wl = lane & 7;
@@ -234,11 +235,14 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
         }
         if (d < d_pad) {
           float* pd = s_depth + wl * CS + d * kCgRows + hl;
-          float* pg = s_dg + wl * CS + d * kCgRows + hl;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             pd[4 * k] = (r[u][k] >= 0 && r[u][k] == lead) ? dv[u][k] : 0.f;
-            pg[4 * k] = 0.f;
+            // depth_grad of a dropped point is 0 and nobody else writes it: stored here, 8 consecutive w per (d, h);
+            // every kept point is written exactly once by the item that owns it (main loop or slow path)
+            const int h = h0 + 4 * k + hl;
+            if (r[u][k] < 0 && w_in && h < prm.h && d < prm.d)
+              Vec4<T>::store1s(depth_grad, img_base + (int64_t)d * hw + h * prm.w + w0 + wl, 0.f);
           }
           if (hl == 0) {
             s_lead[wl * d_pad + d] = kept ? lead : -1;
@@ -267,7 +271,7 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
     const int* lead_col = s_lead + warp * d_pad;
     int* items = s_items + warp * d_pad;
     const float* depth_col = s_depth + warp * CS + 4 * rg;
-    float* dg_col = s_dg + warp * CS;
+    T* dg_col = depth_grad + img_base + (int64_t)h0 * prm.w + ww;   // + bin * hw + row * W
     T* ring = s_R + (size_t)warp * kCgStages * kCgChunk * C;
     uint64_t* full = s_full + warp * kCgStages;
 
@@ -323,7 +327,7 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
         run_item(slice_load<T, K4, K2, false>(rows + (size_t)(2 * pr + 1) * C, cg), rec_b & 255, db);
         const float dot = reduce_pair(da, db, cg);
         const int mine = (cg & 4) ? rec_b : rec_a;
-        if ((mine >> (8 + my_row)) & 1) dg_col[(mine & 255) * kCgRows + my_row] = dot;
+        if ((mine >> (8 + my_row)) & 1) Vec4<T>::store1(dg_col, (int64_t)(mine & 255) * hw + my_row * prm.w, dot);
       }
       __syncwarp();   // every lane is done with this stage before the next issue() refills it
     }
@@ -336,7 +340,7 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
       const float db[4] = {0.f, 0.f, 0.f, 0.f};
       run_item(slice_load<T, K4, K2, false>(rowp, cg), rec & 255, da);
       const float dot = reduce_pair(da, db, cg);
-      if (!(cg & 4) && ((rec >> (8 + my_row)) & 1)) dg_col[(rec & 255) * kCgRows + my_row] = dot;
+      if (!(cg & 4) && ((rec >> (8 + my_row)) & 1)) Vec4<T>::store1(dg_col, (int64_t)(rec & 255) * hw + my_row * prm.w, dot);
     }
 
     // ---- slow path: bins whose kept rows sit in more than one voxel; one extra item per additional voxel, its
@@ -364,7 +368,7 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
                        : 0.f;
           item_fma<K4, K2>(slice_load<T, K4, K2, true>(og + (int64_t)rank * C, cg), w, fv, fg, da);
           const float dot = reduce_pair(da, db, cg);
-          if (!(cg & 4) && ((mask >> my_row) & 1)) dg_col[bin * kCgRows + my_row] = dot;
+          if (!(cg & 4) && ((mask >> my_row) & 1)) Vec4<T>::store1(dg_col, (int64_t)bin * hw + my_row * prm.w, dot);
         }
       }
     }
@@ -411,18 +415,6 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
         if (K2) RowIO<T>::st2(o + 32 * K4 + 2 * cg, fg[p].t);
       }
   }
-  // ---- depth_grad of the tile, zeros for dropped points included (s_dg is not aliased by the tile)
-  if (w0 + wl < prm.w) {
-    for (int d = warp; d < prm.d; d += kCgWarps) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int trow = 4 * k + hl;
-        if (h0 + trow < prm.h)
-          Vec4<T>::store1s(depth_grad, img_base + (int64_t)d * hw + (h0 + trow) * prm.w + w0 + wl,
-                           s_dg[wl * CS + d * kCgRows + trow]);
-      }
-    }
-  }
 }
 
 template <typename T, int K4, bool K2>
@@ -432,12 +424,13 @@ static int backward_column_launch(const void* og, void* dg, void* fg, const void
   const size_t d_pad = (size_t)((prm.d + 7) & ~7);
   const size_t col_bytes = sizeof(float) * kCgW * (d_pad * kCgRows + 4);
   const size_t ring_bytes = sizeof(T) * kCgW * kCgStages * kCgChunk * C;
-  const size_t main_bytes = 2 * col_bytes + ring_bytes + sizeof(uint64_t) * kCgW * kCgStages + 2 * sizeof(int) * kCgW * d_pad;
-  const size_t tile_bytes = prm.feat_grad_nchw ? col_bytes + sizeof(float) * C * (kCgRows * kCgW + 1) : 0;
+  const size_t main_bytes = col_bytes + ring_bytes + sizeof(uint64_t) * kCgW * kCgStages + 2 * sizeof(int) * kCgW * d_pad;
+  const size_t tile_bytes = prm.feat_grad_nchw ? sizeof(float) * C * (kCgRows * kCgW + 1) : 0;
   const size_t smem = main_bytes > tile_bytes ? main_bytes : tile_bytes;
-  // Two CTAs (16 warps) per SM are what keeps the FMA pipe fed: a tile too deep for that (D > ~64 in fp32) is left
-  // to the joint kernel, which measured faster there (profiles/r2_ncu_bwd_column.md).
-  if (smem > 113 * 1024) return BEVPOOL_ERR_BAD_ARG;
+  // Two CTAs (16 warps) per SM are what keeps the FMA pipe fed. Measured dispatch rule: on deep frusta (cfg 3: D = 118,
+  // 32 x 88 features, 2 112 CTAs) the joint kernel is faster even when the tile fits twice per SM (bf16: 152 vs 169 us,
+  // fp32 at one CTA per SM: 146 vs 185-227 us), so tiles deeper than 64 bins stay with it (profiles/r2_ncu_bwd_column.md).
+  if (smem > 113 * 1024 || prm.d > 64) return BEVPOOL_ERR_BAD_ARG;
   const int blocks_w = (prm.w + kCgW - 1) / kCgW, blocks_h = (prm.h + kCgRows - 1) / kCgRows;
   if (blocks_h > 65535 || bn > 65535) return BEVPOOL_ERR_OVERFLOW;
   auto kern = pool_bwd_column_kernel<T, K4, K2>;
