@@ -5,7 +5,8 @@
  * sizes (no torch types), launches hand-written CUDA kernels asynchronously on the
  * stream the caller passes (a cudaStream_t cast to void*; NULL = legacy default
  * stream) and returns 0 or a negative bevpool_status / positive cudaError_t.
- * Nothing here synchronises the device and nothing falls back to the CPU.
+ * Nothing here synchronises the device (bevpool_prepare_v2_counts alone waits for one 8-byte copy) and nothing
+ * falls back to the CPU.
  *
  * Reference interfaces replaced (paths relative to
  * /root/reference/projects/mmdet3d_plugin):
@@ -17,6 +18,7 @@
  *   bevpool_v2_backward_regroup   ops/bev_pool_v2/bev_pool.py:47-57        argsort by ranks_feat + run-length
  *   bevpool_geometry              bevfusion/detectors/cam_stream_lss_bevpoolv2.py:244-251  get_geometry
  *   bevpool_prepare_v2            same file :294-351                        voxel_pooling_prepare_v2
+ *   bevpool_prepare_v2_counts     same file :324-351                        ... with its exact-length outputs
  *   bevpool_voxel_table +         the fused forms of the above used by the view-transform shim:
  *   bevpool_v2_forward_dense /    bev_pool.py:27 (zeros) + :29 (kernel) + :91 (permute) in one pass;
  *   bevpool_v2_backward_dense     bev_pool.py:47-57,67-70 (argsort, zeros, kernel) in one pass
@@ -126,6 +128,19 @@ int bevpool_prepare_v2(const float* coor, const float* frustum, const float* rot
                        int32_t* interval_starts, int32_t* interval_lengths,
                        int32_t* counts_dev, int32_t* point_rank,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same work, plus the two counts handed back to the HOST (host_counts[0] = P, host_counts[1] = I) — what the
+ * reference API needs to return exact-length tensors (cam_stream_lss_bevpoolv2.py:324-351 reads them through
+ * boolean-mask indexing and torch.where). P is final after the rank kernel and I equals the number of occupied
+ * voxels (a bitmap filled by the same kernel), so the 8-byte copy is queued BEFORE the sort and the segmentation:
+ * the call returns as soon as that copy has landed, with the remaining kernels still running on `stream`.
+ * This is the only entry point that waits for the device; it refuses a capturing stream (BEVPOOL_ERR_BAD_ARG). */
+int bevpool_prepare_v2_counts(const float* coor, const float* frustum, const float* rots, const float* trans,
+                              const bevpool_grid_t* g,
+                              int32_t* ranks_bev, int32_t* ranks_depth, int32_t* ranks_feat,
+                              int32_t* interval_starts, int32_t* interval_lengths,
+                              int32_t* counts_dev, int32_t* point_rank,
+                              void* workspace, size_t workspace_bytes, void* stream, int32_t* host_counts);
 
 /* ------------------------------------------------------------------ fused ("dense") pooling
  * Lower-bound table over the sorted voxel ranks: vox_pt[v] = number of sorted points with rank < v,

@@ -38,6 +38,8 @@ SIGNATURES = {
     "bevpool_prepare_v2_workspace_bytes": (c_size_t, [ctypes.POINTER(GridT)]),
     "bevpool_prepare_v2": (c_int, [c_void_p] * 4 + [ctypes.POINTER(GridT)] + [c_void_p] * 7 +
                            [c_void_p, c_size_t, c_void_p]),
+    "bevpool_prepare_v2_counts": (c_int, [c_void_p] * 4 + [ctypes.POINTER(GridT)] + [c_void_p] * 7 +
+                                  [c_void_p, c_size_t, c_void_p, ctypes.POINTER(ctypes.c_int32 * 2)]),
     "bevpool_voxel_table": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p]),
     "bevpool_v2_forward_dense_scratch_bytes": (c_size_t, [c_i64, c_i64, c_int, c_int, c_int]),
     "bevpool_v2_forward_dense": (c_int, [c_void_p] * 7 + [c_i64, c_void_p, c_int, c_i64, c_i64, c_int, c_int, c_int,

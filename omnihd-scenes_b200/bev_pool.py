@@ -56,27 +56,40 @@ def _require_cuda(name, t):
         raise ValueError(f"{name} must be a CUDA tensor (bevpool_b200 has no CPU path)")
 
 
-def _canon_inputs(depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths):
-    """Casts of bev_pool.py:19-25. fp32 unless BOTH depth and feat are bf16 (explicit extension)."""
-    for n, t in (("depth", depth), ("feat", feat), ("ranks_depth", ranks_depth), ("ranks_feat", ranks_feat),
-                 ("ranks_bev", ranks_bev), ("interval_starts", interval_starts),
-                 ("interval_lengths", interval_lengths)):
-        _require_cuda(n, t)
-        if t.device != depth.device:
-            raise ValueError(f"{n} is on {t.device}, depth on {depth.device}")
+def _canon_floats(depth, feat):
+    """Casts of bev_pool.py:19-20. fp32 unless BOTH depth and feat are bf16 (explicit extension)."""
+    _require_cuda("depth", depth)
+    _require_cuda("feat", feat)
+    if feat.device != depth.device:
+        raise ValueError(f"feat is on {feat.device}, depth on {depth.device}")
     if depth.dtype == torch.bfloat16 and feat.dtype == torch.bfloat16:
         depth, feat = depth.contiguous(), feat.contiguous()
     else:
         depth, feat = depth.contiguous().float(), feat.contiguous().float()
+    if feat.dim() < 1 or feat.shape[-1] <= 0:
+        raise ValueError("feat must be [..., C] with C > 0 (channels last)")
+    return depth, feat
+
+
+def _canon_ints(device, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths):
+    """Casts of bev_pool.py:21-25 + the consistency checks the reference leaves to its kernel."""
+    for n, t in (("ranks_depth", ranks_depth), ("ranks_feat", ranks_feat), ("ranks_bev", ranks_bev),
+                 ("interval_starts", interval_starts), ("interval_lengths", interval_lengths)):
+        _require_cuda(n, t)
+        if t.device != device:
+            raise ValueError(f"{n} is on {t.device}, depth on {device}")
     ints = [t.contiguous().int() for t in (ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths)]
     n_points = ints[0].numel()
     if ints[1].numel() != n_points or ints[2].numel() != n_points:
         raise ValueError("ranks_depth, ranks_feat and ranks_bev must have the same length")
     if ints[3].numel() != ints[4].numel():
         raise ValueError("interval_starts and interval_lengths must have the same length")
-    if feat.dim() < 1 or feat.shape[-1] <= 0:
-        raise ValueError("feat must be [..., C] with C > 0 (channels last)")
-    return (depth, feat) + tuple(ints)
+    return tuple(ints)
+
+
+def _canon_inputs(depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths):
+    depth, feat = _canon_floats(depth, feat)
+    return (depth, feat) + _canon_ints(depth.device, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths)
 
 
 def _shape5(bev_feat_shape, feat):
@@ -98,29 +111,32 @@ class PreparePlan:
 
     point_rank[P0] (voxel rank of every frustum point, -1 = dropped) is the inverse table
     that lets the backward walk a pixel's depth bins without sorting by ranks_feat.
+    The plan rides on the `ranks_bev` tensor object itself (a Python attribute: it lives and dies with that
+    tensor, no registry) and is honoured only if all five tensors are the very objects prepare returned, unmodified.
     """
+    __slots__ = ("others", "versions", "point_rank", "bn", "d", "h", "w", "hw")
 
     def __init__(self, tensors, point_rank, bn, d, h, w):
-        self.refs = [weakref.ref(t) for t in tensors]
-        self.versions = [t._version for t in tensors]
+        self.others = tuple(tensors[1:])
+        self.versions = tuple(t._version for t in tensors)
         self.point_rank, self.bn, self.d, self.h, self.w, self.hw = point_rank, bn, d, h, w, h * w
 
     def matches(self, tensors):
-        return all(r() is t and t._version == v for r, t, v in zip(self.refs, tensors, self.versions))
+        o, v = self.others, self.versions
+        return (tensors[1] is o[0] and tensors[2] is o[1] and tensors[3] is o[2] and tensors[4] is o[3] and
+                all(t._version == ver for t, ver in zip(tensors, v)))
 
 
-_PLANS = {}
+_PLAN_ATTR = "_bevpool_b200_plan"
 
 
 def register_plan(ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths, point_rank, bn, d, h, w):
-    tensors = (ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths)
-    key = id(ranks_bev)
-    _PLANS[key] = PreparePlan(tensors, point_rank, bn, d, h, w)
-    weakref.finalize(ranks_bev, _PLANS.pop, key, None)
+    setattr(ranks_bev, _PLAN_ATTR, PreparePlan((ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths),
+                                                 point_rank, bn, d, h, w))
 
 
 def _find_plan(ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths, depth, feat):
-    plan = _PLANS.get(id(ranks_bev))
+    plan = getattr(ranks_bev, _PLAN_ATTR, None)
     if plan is None or not plan.matches((ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths)):
         return None
     if depth.numel() != plan.bn * plan.d * plan.hw or feat.numel() != plan.bn * plan.hw * feat.shape[-1]:
@@ -229,13 +245,18 @@ def _column_hint(Z):
     return 1 if Z == 1 else 0
 
 
-def _backward_dense(out_grad_cl, depth, feat, plan, column_hint):
+def _backward_dense(out_grad_cl, depth, feat, plan, column_hint, feat_nchw=False):
+    """feat is channels-last [..., H, W, C]; feat_nchw: write feat_grad as [..., C, H, W] instead."""
     lib = _lib.load()
     depth_grad = torch.empty_like(depth)
-    feat_grad = torch.empty_like(feat)
+    if feat_nchw:
+        feat_grad = feat.new_empty(feat.shape[:-3] + (feat.shape[-1], feat.shape[-3], feat.shape[-2]))
+    else:
+        feat_grad = torch.empty_like(feat)
     _lib.check(lib.bevpool_v2_backward_dense(_ptr(out_grad_cl), _ptr(depth_grad), _ptr(feat_grad), _ptr(depth),
                                              _ptr(feat), _ptr(plan.point_rank), plan.bn, plan.d, plan.h, plan.w,
-                                             feat.shape[-1], 0, 1 if column_hint else 0, _dtype_code(feat), _stream()),
+                                             feat.shape[-1], 1 if feat_nchw else 0, 1 if column_hint else 0,
+                                             _dtype_code(feat), _stream()),
                "bevpool_v2_backward_dense")
     return depth_grad, feat_grad
 
@@ -263,6 +284,19 @@ class QuickCumsumCuda(torch.autograd.Function):
         return depth_grad, feat_grad, None, None, None, None, None, None
 
 
+def _nchw_view_of(feat, depth):
+    """The reference hands bev_pool_v2 `feat.permute(0, 1, 3, 4, 2)` of the neck's [B,N,C,H,W] tensor
+    (cam_stream_lss_bevpoolv2.py:282) and lets `.contiguous()` copy it (bev_pool.py:20). If `feat` is such a view,
+    return the contiguous [B,N,C,H,W] tensor behind it: our transpose kernel then makes the channels-last copy, and
+    the sort-free backward writes the gradient straight back in [B,N,C,H,W] (returned as the same permuted view)."""
+    if feat.dim() != 5 or feat.is_contiguous():
+        return None
+    if not (feat.dtype == torch.float32 or (feat.dtype == torch.bfloat16 and depth.dtype == torch.bfloat16)):
+        return None
+    v = feat.permute(0, 1, 4, 2, 3)
+    return v if v.is_contiguous() else None
+
+
 class _BevPoolV2Fused(torch.autograd.Function):
     """bev_pool_v2 as one fused pass: returns [B, C, Z, Y, X] directly."""
 
@@ -271,12 +305,25 @@ class _BevPoolV2Fused(torch.autograd.Function):
                 interval_lengths):
         plan_key = (ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths)
         in_depth_dtype, in_feat_dtype = depth.dtype, feat.dtype
-        depth, feat, rd, rf, rb, starts, lengths = _canon_inputs(depth, feat, ranks_depth, ranks_feat, ranks_bev,
-                                                                 interval_starts, interval_lengths)
+        _require_cuda("feat", feat)
+        nchw = _nchw_view_of(feat, depth)
+        if nchw is not None:
+            Bf, Nf, Cf, Hf, Wf = nchw.shape
+            feat = nchw.new_empty((Bf, Nf, Hf, Wf, Cf))
+            if feat.numel():
+                _launch_transpose(nchw, feat, Bf * Nf, Cf, Hf * Wf, True)       # [BN,C,HW] -> [BN,HW,C]
+        depth, feat = _canon_floats(depth, feat)
+        ctx.plan = _find_plan(*plan_key, depth, feat) if isinstance(ranks_bev, torch.Tensor) else None
+        if ctx.plan is not None and ranks_bev.device == depth.device:
+            rd, rf, rb, starts, lengths = ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths
+        else:       # foreign rank tensors: casts and checks
+            ctx.plan = None
+            rd, rf, rb, starts, lengths = _canon_ints(depth.device, ranks_depth, ranks_feat, ranks_bev, interval_starts,
+                                                      interval_lengths)
         B, Z, Y, X, C = _shape5(bev_feat_shape, feat)
-        ctx.plan = _find_plan(*plan_key, depth, feat)
         ctx.shape = (B, Z, Y, X, C)
         ctx.in_dtypes = (in_depth_dtype, in_feat_dtype)
+        ctx.nchw = nchw is not None
         # the fused kernel walks the sorted point list by voxel. Tensors that came from our prepare are canonical by
         # construction; anything else is verified on the device (see _intervals_are_canonical).
         fused_ok = C % 4 == 0 and rb.numel() > 0 and feat.data_ptr() % 16 == 0 and \
@@ -303,7 +350,10 @@ class _BevPoolV2Fused(torch.autograd.Function):
         og_cl = out_grad.new_empty((B, Z, Y, X, C))
         _launch_transpose(out_grad, og_cl, B, C, Z * Y * X, to_channels_last=True)
         if ctx.plan is not None and C % 4 == 0:
-            depth_grad, feat_grad = _backward_dense(og_cl, depth, feat, ctx.plan, column_hint=_column_hint(Z))
+            depth_grad, feat_grad = _backward_dense(og_cl, depth, feat, ctx.plan, column_hint=_column_hint(Z),
+                                                    feat_nchw=ctx.nchw)
+            if ctx.nchw:
+                feat_grad = feat_grad.permute(0, 1, 3, 4, 2)
         else:
             depth_grad, feat_grad = _backward_general(og_cl, depth, feat, rd, rf, rb)
         return depth_grad.to(ctx.in_dtypes[0]), feat_grad.to(ctx.in_dtypes[1]), None, None, None, None, None, None

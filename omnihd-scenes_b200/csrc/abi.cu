@@ -4,6 +4,7 @@
 #include <mutex>
 #include <stdlib.h>
 #include <utility>
+#include <vector>
 
 #include "common.cuh"
 
@@ -35,6 +36,40 @@ int ensure_dynamic_smem_impl(const void* kern, size_t smem) {
   if (e != cudaSuccess) return (int)e;
   have = smem;
   return 0;
+}
+
+// Pinned 8-byte landing slots + events for the one entry point that hands counts back to the host
+// (bevpool_prepare_v2_counts). Slots are recycled; events are per device.
+static std::mutex g_slot_mu;
+static std::vector<CountSlot*> g_free_slots;
+
+CountSlot* acquire_count_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_slot_mu);
+    for (size_t i = 0; i < g_free_slots.size(); ++i)
+      if (g_free_slots[i]->dev == dev) {
+        CountSlot* s = g_free_slots[i];
+        g_free_slots.erase(g_free_slots.begin() + i);
+        return s;
+      }
+  }
+  CountSlot* s = new CountSlot;
+  s->dev = dev;
+  s->host = nullptr;
+  if (cudaHostAlloc((void**)&s->host, 2 * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming) != cudaSuccess) {
+    if (s->host) cudaFreeHost(s->host);
+    delete s;
+    return nullptr;
+  }
+  return s;
+}
+
+void release_count_slot(CountSlot* s) {
+  std::lock_guard<std::mutex> lock(g_slot_mu);
+  g_free_slots.push_back(s);
 }
 }  // namespace bevpool
 

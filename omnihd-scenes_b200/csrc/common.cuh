@@ -40,6 +40,15 @@ __device__ __forceinline__ void pdl_wait() {
 
 bool pdl_enabled();   // abi.cu (BEVPOOL_PDL=0 disables)
 
+// Pinned landing slot + event for a small device->host hand-back inside one entry point (abi.cu)
+struct CountSlot {
+  int32_t* host;      // 2 x int32, page-locked
+  cudaEvent_t ev;
+  int dev;
+};
+CountSlot* acquire_count_slot();   // nullptr on failure
+void release_count_slot(CountSlot* s);
+
 // Opt a kernel in to `smem` bytes of dynamic shared memory (> 48 KB) on the CURRENT device; cached per
 // (kernel, device). Returns 0 or the cudaError_t.
 int ensure_dynamic_smem_impl(const void* kern, size_t smem);   // abi.cu

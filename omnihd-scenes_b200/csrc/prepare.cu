@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kSortThreads)
 point_rank_kernel(const float* __restrict__ coor, const float* __restrict__ frustum, const float* __restrict__ rots,
                   const float* __restrict__ trans, GridDev g, SortPlan plan, int* __restrict__ point_rank,
                   uint32_t* __restrict__ tile_hist0, uint32_t* __restrict__ totals /*[kMaxPasses][kMaxBins]*/,
-                  int* __restrict__ n_kept) {
+                  int* __restrict__ n_kept, uint32_t* __restrict__ occupied /* voxel bitmap or nullptr */) {
   extern __shared__ float s_cam[];                       // [bn][12] (fused geometry only)
   __shared__ uint32_t sh[kMaxPasses][kMaxBins];
   __shared__ uint32_t s_kept;
@@ -183,6 +183,7 @@ point_rank_kernel(const float* __restrict__ coor, const float* __restrict__ frus
 #pragma unroll
         for (int p = 0; p < kMaxPasses; ++p)
           if (p < plan.n_passes) atomicAdd(&sh[p][(rank >> plan.shift[p]) & ((1 << plan.bits[p]) - 1)], 1u);
+        if (occupied) atomicOr(occupied + (rank >> 5), 1u << (rank & 31));
       }
       point_rank[idx] = rank;
     }
@@ -223,6 +224,27 @@ key_hist_kernel(const int* __restrict__ keys, int64_t n, SortPlan plan, uint32_t
   for (int i = tid; i < plan.n_passes * kMaxBins; i += kSortThreads) {
     const uint32_t v = (&sh[0][0])[i];
     if (v) atomicAdd(totals + i, v);
+  }
+}
+
+// Early counts for the host (bevpool_prepare_v2_counts): P is final once the rank kernel is done, and the number
+// of intervals equals the number of occupied voxels — no need to wait for the sort and the segmentation.
+__global__ void __launch_bounds__(256)
+early_counts_kernel(const uint32_t* __restrict__ occupied, int64_t words, const int* __restrict__ n_kept,
+                    int* __restrict__ early /*[2], zeroed*/) {
+  pdl_wait();
+  __shared__ uint32_t s_sum;
+  if (threadIdx.x == 0) s_sum = 0;
+  __syncthreads();
+  uint32_t mine = 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < words; i += (int64_t)gridDim.x * 256) mine += __popc(occupied[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(kFullMask, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_sum, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_sum) atomicAdd(early + 1, (int)s_sum);
+    if (blockIdx.x == 0) early[0] = *n_kept;
   }
 }
 
@@ -572,25 +594,33 @@ static int check_grid(const bevpool_grid_t* g, int64_t* p0, int64_t* total_voxel
   return BEVPOOL_OK;
 }
 
+// early-count region of the prepare workspace: [2] counts + voxel bitmap, behind the private point_rank array
+static size_t early_region_bytes(int64_t v) { return 256 + align_up(sizeof(uint32_t) * (size_t)((v + 31) / 32), 256); }
+
 extern "C" size_t bevpool_prepare_v2_workspace_bytes(const bevpool_grid_t* g) {
   int64_t p0, v;
   if (check_grid(g, &p0, &v) != BEVPOOL_OK) return 0;
   if (p0 == 0) return 256;
   const SortPlan plan = make_plan(v > 0 ? v - 1 : 0, p0);
-  // + a private point_rank array in case the caller does not want one
-  return carve(nullptr, p0, plan).total_bytes + align_up(sizeof(int) * (size_t)p0, 256);
+  // + a private point_rank array in case the caller does not want one + the early-count region
+  return carve(nullptr, p0, plan).total_bytes + align_up(sizeof(int) * (size_t)p0, 256) + early_region_bytes(v);
 }
 
-extern "C" int bevpool_prepare_v2(const float* coor, const float* frustum, const float* rots, const float* trans,
-                                  const bevpool_grid_t* g, int32_t* ranks_bev, int32_t* ranks_depth,
-                                  int32_t* ranks_feat, int32_t* interval_starts, int32_t* interval_lengths,
-                                  int32_t* counts_dev, int32_t* point_rank, void* workspace, size_t workspace_bytes,
-                                  void* stream) {
+static int prepare_impl(const float* coor, const float* frustum, const float* rots, const float* trans,
+                        const bevpool_grid_t* g, int32_t* ranks_bev, int32_t* ranks_depth, int32_t* ranks_feat,
+                        int32_t* interval_starts, int32_t* interval_lengths, int32_t* counts_dev, int32_t* point_rank,
+                        void* workspace, size_t workspace_bytes, void* stream, int32_t* host_counts) {
   int64_t p0, v;
   int rc = check_grid(g, &p0, &v);
   if (rc != BEVPOOL_OK) return rc;
   if (!counts_dev) return BEVPOOL_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  if (host_counts) {
+    host_counts[0] = host_counts[1] = 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
+      return BEVPOOL_ERR_BAD_ARG;                     // a host hand-back cannot be captured into a graph
+  }
   cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int32_t), st);
   if (p0 == 0) return launch_status();
   if (!ranks_bev || !ranks_depth || !workspace) return BEVPOOL_ERR_BAD_ARG;
@@ -602,6 +632,16 @@ extern "C" int bevpool_prepare_v2(const float* coor, const float* frustum, const
   const SortWorkspace w = carve(workspace, p0, plan);
   if (!point_rank) point_rank = (int*)((char*)workspace + w.total_bytes);
   cudaMemsetAsync(workspace, 0, w.zero_bytes, st);
+  int* early = nullptr;
+  uint32_t* occupied = nullptr;
+  CountSlot* slot = nullptr;
+  if (host_counts) {
+    early = (int*)((char*)workspace + w.total_bytes + align_up(sizeof(int) * (size_t)p0, 256));
+    occupied = (uint32_t*)((char*)early + 256);
+    cudaMemsetAsync(early, 0, early_region_bytes(v), st);
+    slot = acquire_count_slot();
+    if (!slot) return (int)cudaErrorMemoryAllocation;
+  }
 
   GridDev gd;
   gd.n_points = p0;
@@ -618,16 +658,29 @@ extern "C" int bevpool_prepare_v2(const float* coor, const float* frustum, const
     gd.inv[a] = exact_reciprocal_or_zero(g->dx[a]);
   }
   if (coor) {
-    point_rank_kernel<true><<<(unsigned)plan.n_tiles, kSortThreads, 0, st>>>(coor, frustum, rots, trans, gd, plan,
-                                                                            point_rank, w.hist0, w.totals, counts_dev);
+    point_rank_kernel<true><<<(unsigned)plan.n_tiles, kSortThreads, 0, st>>>(
+        coor, frustum, rots, trans, gd, plan, point_rank, w.hist0, w.totals, counts_dev, occupied);
   } else {
     const size_t cam_smem = sizeof(float) * 12 * (size_t)gd.bn;
     // ~9 KB of static shared memory on top of the camera table: opt in as soon as the TOTAL passes 48 KB
-    if (int rc = ensure_dynamic_smem(point_rank_kernel<false>, cam_smem + 9 * 1024)) return rc;
+    if (int rc = ensure_dynamic_smem(point_rank_kernel<false>, cam_smem + 9 * 1024)) {
+      if (slot) release_count_slot(slot);
+      return rc;
+    }
     point_rank_kernel<false><<<(unsigned)plan.n_tiles, kSortThreads, cam_smem, st>>>(
-        coor, frustum, rots, trans, gd, plan, point_rank, w.hist0, w.totals, counts_dev);
+        coor, frustum, rots, trans, gd, plan, point_rank, w.hist0, w.totals, counts_dev, occupied);
   }
   count_launch();
+  if (slot) {
+    // counts leave for the host now; everything below is queued behind them and the host waits for the copy only
+    const int64_t words = (v + 31) / 32;
+    int eb = (int)((words + 255) / 256);
+    if (eb > kNumSMs * 4) eb = kNumSMs * 4;
+    early_counts_kernel<<<eb, 256, 0, st>>>(occupied, words, counts_dev, early);
+    count_launch();
+    cudaMemcpyAsync(slot->host, early, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(slot->ev, st);
+  }
 
   run_passes(plan, w, point_rank, nullptr, p0, counts_dev, ranks_bev, ranks_depth, st);
 
@@ -648,7 +701,37 @@ extern "C" int bevpool_prepare_v2(const float* coor, const float* frustum, const
                (const int*)counts_dev, (int64_t)p0, interval_lengths);
     count_launch(3);
   }
-  return launch_status();
+  rc = launch_status();
+  if (slot) {
+    const cudaError_t e = cudaEventSynchronize(slot->ev);
+    if (e == cudaSuccess) {
+      host_counts[0] = slot->host[0];
+      host_counts[1] = slot->host[1];
+    } else if (rc == BEVPOOL_OK) {
+      rc = (int)e;
+    }
+    release_count_slot(slot);
+  }
+  return rc;
+}
+
+extern "C" int bevpool_prepare_v2(const float* coor, const float* frustum, const float* rots, const float* trans,
+                                  const bevpool_grid_t* g, int32_t* ranks_bev, int32_t* ranks_depth,
+                                  int32_t* ranks_feat, int32_t* interval_starts, int32_t* interval_lengths,
+                                  int32_t* counts_dev, int32_t* point_rank, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  return prepare_impl(coor, frustum, rots, trans, g, ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths,
+                      counts_dev, point_rank, workspace, workspace_bytes, stream, nullptr);
+}
+
+extern "C" int bevpool_prepare_v2_counts(const float* coor, const float* frustum, const float* rots, const float* trans,
+                                         const bevpool_grid_t* g, int32_t* ranks_bev, int32_t* ranks_depth,
+                                         int32_t* ranks_feat, int32_t* interval_starts, int32_t* interval_lengths,
+                                         int32_t* counts_dev, int32_t* point_rank, void* workspace,
+                                         size_t workspace_bytes, void* stream, int32_t* host_counts) {
+  if (!host_counts) return BEVPOOL_ERR_BAD_ARG;
+  return prepare_impl(coor, frustum, rots, trans, g, ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths,
+                      counts_dev, point_rank, workspace, workspace_bytes, stream, host_counts);
 }
 
 extern "C" size_t bevpool_v2_backward_regroup_workspace_bytes(int64_t n_points) {

@@ -14,6 +14,7 @@ voxel_pooling_v2 and s2c — without the conv nets around them (out of scope).
 
 Device work is done by csrc/prepare.cu and csrc/pool.cu through the C ABI.
 """
+import ctypes
 import os
 
 import torch
@@ -120,12 +121,20 @@ def get_geometry(frustum, rots, trans):
 # ----------------------------------------------------------------------------- prepare
 class _Prepared:
     """Worst-case-sized device outputs of one prepare call (no host sync yet)."""
-    __slots__ = ("rb", "rd", "rf", "starts", "lengths", "counts", "point_rank", "bn", "d", "h", "w", "hw", "p0")
+    __slots__ = ("rb", "rd", "rf", "starts", "lengths", "counts", "point_rank", "bn", "d", "h", "w", "hw", "p0",
+                 "host_counts")
 
 
-def _prepare_device(coor, frustum, rots, trans, B, N, D, H, W, dx, bx, nx, device, want_intervals=True):
+def _pad64(n):
+    return (max(n, 1) + 63) // 64 * 64            # rows stay 256-byte aligned (128-bit loads)
+
+
+def _prepare_device(coor, frustum, rots, trans, B, N, D, H, W, dx, bx, nx, device, want_intervals=True,
+                    host_counts=False):
     """want_intervals=False (fused path): only the sorted (ranks_bev, ranks_depth) lists, the kept count and
-    point_rank are produced — ranks_feat is derivable and the interval arrays are replaced by the voxel table."""
+    point_rank are produced — ranks_feat is derivable and the interval arrays are replaced by the voxel table.
+    host_counts=True (API path): `bevpool_prepare_v2_counts` — the call hands (P, I) back as soon as the rank
+    kernel has run, with the sort still in flight; they are left in `out.host_counts`."""
     lib = _lib.load()
     g = _grid_struct(B, N, D, H, W, dx, bx, nx)
     p0 = B * N * D * H * W
@@ -133,31 +142,44 @@ def _prepare_device(coor, frustum, rots, trans, B, N, D, H, W, dx, bx, nx, devic
     if p0 >= 2 ** 30 or vtot >= 2 ** 31 - 1:
         raise ValueError("problem too large for int32 ranks: shard the frame batch")
     out = _Prepared()
-    pad = lambda n: (max(n, 1) + 63) // 64 * 64            # rows stay 256-byte aligned (128-bit loads)
-    ranks = torch.empty((3 if want_intervals else 2, pad(p0)), dtype=torch.int32, device=device)[:, :max(p0, 1)]
-    out.rb, out.rd = ranks[0], ranks[1]
+    # one int32 block: [ranks_bev | ranks_depth | (ranks_feat) | (starts | lengths) | counts]; point_rank is its own
+    # tensor (the fused path keeps only that one alive until the backward)
+    pp, n1 = _pad64(p0), max(p0, 1)
+    rows = 3 if want_intervals else 2
+    n_int = max(min(p0, vtot), 1) if want_intervals else 0
+    pi = _pad64(n_int) if want_intervals else 0
+    o_int = rows * pp
+    o_cnt = o_int + 2 * pi
+    blk = torch.empty(o_cnt + 64, dtype=torch.int32, device=device)
+    base = blk.data_ptr()
+    p_rf = p_st = p_ln = None
+    if want_intervals:
+        p_rf, p_st, p_ln = base + 8 * pp, base + 4 * o_int, base + 4 * (o_int + pi)
+    out.point_rank = torch.empty(n1, dtype=torch.int32, device=device)
+    out.bn, out.d, out.h, out.w, out.hw, out.p0 = B * N, D, H, W, H * W, p0
+    ws_bytes = max(lib.bevpool_prepare_v2_workspace_bytes(g), 256)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+    args = (_ptr(coor), _ptr(frustum), _ptr(rots), _ptr(trans), ctypes.byref(g), base, base + 4 * pp, p_rf, p_st, p_ln,
+            base + 4 * o_cnt, out.point_rank.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+    n_r, n_i = n1, n_int                     # worst-case lengths unless the host learns the counts
+    if host_counts:
+        hc = (ctypes.c_int32 * 2)()
+        _lib.check(lib.bevpool_prepare_v2_counts(*args, ctypes.byref(hc)), "bevpool_prepare_v2_counts")
+        out.host_counts = n_r, n_i = hc[0], hc[1]
+    else:
+        _lib.check(lib.bevpool_prepare_v2(*args), "bevpool_prepare_v2")
+        out.host_counts = None
+    out.rb, out.rd = blk[:n_r], blk[pp:pp + n_r]
     out.rf = out.starts = out.lengths = None
     if want_intervals:
-        n_int = max(min(p0, vtot), 1)
-        inter = torch.empty((2, pad(n_int)), dtype=torch.int32, device=device)[:, :n_int]
-        out.rf = ranks[2]
-        out.starts, out.lengths = inter[0], inter[1]
-    out.counts = torch.empty(2, dtype=torch.int32, device=device)
-    out.point_rank = torch.empty(max(p0, 1), dtype=torch.int32, device=device)
-    out.bn, out.d, out.h, out.w, out.hw, out.p0 = B * N, D, H, W, H * W, p0
-    ws_bytes = lib.bevpool_prepare_v2_workspace_bytes(g)
-    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=device)
-    import ctypes
-    _lib.check(lib.bevpool_prepare_v2(_ptr(coor), _ptr(frustum), _ptr(rots), _ptr(trans), ctypes.byref(g),
-                                      _ptr(out.rb), _ptr(out.rd), _ptr(out.rf), _ptr(out.starts), _ptr(out.lengths),
-                                      _ptr(out.counts), _ptr(out.point_rank), _ptr(ws), ws.numel(), _stream()),
-               "bevpool_prepare_v2")
+        out.rf = blk[2 * pp:2 * pp + n_r]
+        out.starts, out.lengths = blk[o_int:o_int + n_i], blk[o_int + pi:o_int + pi + n_i]
+    out.counts = blk[o_cnt:o_cnt + 2]
     return out
 
 
 def _view_forward_scatter(depth, feat_cl, out, view, rots, trans, n, N, D, H, W, C, frames, rows, layout):
     """Sort-free forward (csrc/pool_scatter.cu) of `n` frames; returns the _Prepared stub the backward needs."""
-    import ctypes
     lib = _lib.load()
     g = _grid_struct(n, N, D, H, W, view.dx, view.bx, view.nx)
     p0 = n * N * D * H * W
@@ -193,11 +215,15 @@ def voxel_pooling_prepare_v2(coor, dx, bx, nx):
     if B * N * D * H * W == 0:
         return None, None, None, None, None
     coor = coor.contiguous()
-    pr = _prepare_device(coor, None, None, None, B, N, D, H, W, dx, bx, nx, coor.device)
-    P, I = (int(v) for v in pr.counts.tolist())
+    # BEVPOOL_LATE_COUNTS=1 (measurement only): read the counts back after the whole prepare, as round 1 did
+    early = os.environ.get("BEVPOOL_LATE_COUNTS") != "1"
+    pr = _prepare_device(coor, None, None, None, B, N, D, H, W, dx, bx, nx, coor.device, host_counts=early)
+    P, I = pr.host_counts if early else (int(v) for v in pr.counts.tolist())
     if P == 0 or I == 0:
         return None, None, None, None, None
-    res = (pr.rb[:P], pr.rd[:P], pr.rf[:P], pr.starts[:I], pr.lengths[:I])
+    # with early counts the views already have their exact lengths
+    res = (pr.rb, pr.rd, pr.rf, pr.starts, pr.lengths) if early else \
+        (pr.rb[:P], pr.rd[:P], pr.rf[:P], pr.starts[:I], pr.lengths[:I])
     register_plan(*res, pr.point_rank, pr.bn, pr.d, pr.h, pr.w)
     return res
 
@@ -381,14 +407,23 @@ class LSSViewTransform(nn.Module):
     def voxel_pooling_prepare_v2(self, coor):
         return voxel_pooling_prepare_v2(coor, self.dx, self.bx, self.nx)
 
+    def _nx_ints(self):
+        """(X, Y, Z) as Python ints, cached against the identity / version of `self.nx`."""
+        nx = self.nx
+        hit = self.__dict__.get("_nx_cache")
+        if hit is None or hit[0] is not nx or hit[1] != nx._version:
+            hit = self.__dict__["_nx_cache"] = (nx, nx._version, tuple(int(v) for v in nx))
+        return hit[2]
+
     def voxel_pooling_v2(self, coor, depth, feat):
         """coor [B,N,D,H,W,3], depth [B,N,D,H,W], feat [B,N,C,H,W] -> [B,C,Z,Y,X] (or None)."""
         ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths = self.voxel_pooling_prepare_v2(coor)
         if ranks_feat is None:
             print('warning ---> no points within the predefined bev receptive field')
             return None
-        feat = feat.permute(0, 1, 3, 4, 2).contiguous()
-        bev_feat_shape = (depth.shape[0], int(self.nx[2]), int(self.nx[1]), int(self.nx[0]), feat.shape[-1])
+        feat = feat.permute(0, 1, 3, 4, 2)           # a view, as the reference passes it (:282)
+        X, Y, Z = self._nx_ints()
+        bev_feat_shape = (depth.shape[0], Z, Y, X, feat.shape[-1])
         return bev_pool_v2(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
                            interval_lengths)
 

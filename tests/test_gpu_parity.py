@@ -241,6 +241,45 @@ def test_prepare_properties_omnihd_shape(pkg):
     assert all(torch.equal(a, b) for a, b in zip((rb, rd, rf, st, ln), again))
 
 
+@pytest.mark.parametrize("cfg_name,B", [("bevdet_r50_b8", 3), ("occ_200x200x16_b64", 1), ("tiny", 1)])
+def test_prepare_early_host_counts_equal_device_counts(pkg, cfg_name, B, monkeypatch):
+    """bevpool_prepare_v2_counts hands (P, I) to the host from the rank kernel's kept count and voxel bitmap, before
+    the sort has run: they must equal what the sort + segmentation leave in counts_dev, and the late read-back
+    (BEVPOOL_LATE_COUNTS=1) must return the same tensors."""
+    vt = pkg.view_transform
+    dev = torch.device(DEV)
+    if cfg_name == "tiny":      # a handful of points incl. NaN / Inf / out of range, and a case with nothing kept
+        dx, bx, nx = torch.tensor([1., 1., 1.]), torch.tensor([.5, .5, .5]), torch.tensor([4, 4, 1])
+        pts = np.array([[-0.5, 0.2, 0.0], [3.999, 3.5, 0.5], [4.0, 0, 0], [np.nan, 0, 0], [np.inf, 0, 0], [2.5, 2.5, 0.99],
+                        [2.6, 2.4, 0.5], [0.1, 0.1, 0.1]], np.float32).reshape(1, 1, 8, 1, 1, 3)
+        cases = [(cu(pts), dx, bx, nx, (1, 1, 8, 1, 1)), (cu(pts * 0 - 7), dx, bx, nx, (1, 1, 8, 1, 1))]
+    else:
+        cfg = pkg.synthetic.CONFIGS[cfg_name]
+        view = pkg.LSSViewTransform.from_config(cfg).to(DEV)
+        rots, trans = pkg.synthetic.camera_ring(B, cfg.n_cams, cfg.final_dim, seed=11, roll=0.05)
+        coor = view.get_geometry(rots.to(DEV), trans.to(DEV))
+        cases = [(coor, view.dx, view.bx, view.nx, tuple(coor.shape[:5]))]
+    for coor, dx, bx, nx, shp in cases:
+        pr = vt._prepare_device(coor, None, None, None, *shp, dx, bx, nx, dev, host_counts=True)
+        assert tuple(pr.host_counts) == tuple(pr.counts.tolist())
+        early = pkg.voxel_pooling_prepare_v2(coor, dx, bx, nx)
+        monkeypatch.setenv("BEVPOOL_LATE_COUNTS", "1")
+        late = pkg.voxel_pooling_prepare_v2(coor, dx, bx, nx)
+        monkeypatch.delenv("BEVPOOL_LATE_COUNTS")
+        assert all((a is None and b is None) or torch.equal(a, b) for a, b in zip(early, late))
+        if pr.host_counts[0] == 0:
+            assert early[0] is None
+    # a stream under capture cannot hand anything to the host: refused, not deadlocked
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        coor, dx, bx, nx, shp = cases[0]
+        with pytest.raises(pkg._lib.BevPoolError):
+            with torch.cuda.graph(g, stream=side):
+                vt._prepare_device(coor, None, None, None, *shp, dx, bx, nx, dev, host_counts=True)
+    torch.cuda.synchronize()
+
+
 # --------------------------------------------------------------------------------------- forward
 def _forward_cases(pkg, orc, name_or_cfg, B=None, C=None, seed=0):
     if isinstance(name_or_cfg, str) and name_or_cfg.startswith(("tiny", "mid")):
@@ -505,6 +544,32 @@ def test_fused_path_bf16_vs_oracle(pkg, orc, case):
     oracle fed the bf16-rounded inputs, tolerance 2^-8 of max|ref|."""
     cfg, B = _bf16_cases(pkg)[case]
     _view_modes_vs_oracle(pkg, orc, cfg, B, torch.bfloat16, ALL_MODES, seed=3)
+
+
+@pytest.mark.parametrize("cfg_name,B,dt", [("bevdet_r50_b8", 2, torch.float32), ("occ_200x200x16_b64", 1, torch.float32),
+                                           ("bevdet_r50_b8", 2, torch.bfloat16)])
+def test_bev_pool_v2_takes_the_permuted_view_the_reference_passes(pkg, cfg_name, B, dt):
+    """cam_stream_lss_bevpoolv2.py:282 passes `feat.permute(0, 1, 3, 4, 2)` (a view of the neck's [B,N,C,H,W]) and lets
+    bev_pool.py:20 copy it. Our bev_pool_v2 recognises that view (own transpose kernel, gradient written back in
+    [B,N,C,H,W]): values and gradients must equal the contiguous-copy route bit for bit."""
+    cfg = pkg.synthetic.CONFIGS[cfg_name]
+    view = pkg.LSSViewTransform.from_config(cfg).to(DEV)
+    rots, trans = pkg.synthetic.camera_ring(B, cfg.n_cams, cfg.final_dim, seed=4)
+    depth, feat, gout = (t.to(DEV, dt) for t in pkg.synthetic.pool_inputs(cfg, batch=B, seed=4))
+    ranks = view.voxel_pooling_prepare_v2(view.get_geometry(rots.to(DEV), trans.to(DEV)))
+    rb, rd, rf, st, ln = ranks
+    X, Y, Z = (int(v) for v in view.nx)
+    shape = (B, Z, Y, X, cfg.channels)
+    res = []
+    for as_view in (True, False):
+        d, f = depth.clone().requires_grad_(), feat.clone().requires_grad_()
+        fcl = f.permute(0, 1, 3, 4, 2)
+        bev = pkg.bev_pool_v2(d, fcl if as_view else fcl.contiguous(), rd, rf, rb, shape, st, ln)
+        bev.backward(gout)
+        assert f.grad.shape == feat.shape
+        res.append((bev.detach(), d.grad, f.grad))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
 
 
 def test_linearity_and_checksum_full_size(pkg):
