@@ -567,14 +567,18 @@ def run_native_arm(args):
             for ev in evs:
                 ev.record(stream)
 
-        def e2e_step(i):
+        def h2d_of(i):
             k = i % N_BUFFER_SETS
-            s, h, o = sets[k], host[k], out_host[k]
+            s, h = sets[k], host[k]
             with torch.cuda.stream(st_h2d), torch.no_grad():
                 st_h2d.wait_event(ev_cmp[k])          # the previous step on this set has consumed its inputs
                 for dst, src in zip((s["rots"], s["trans"], s["depth"], s["feat"], s["gout"]), h):
                     dst.copy_(src, non_blocking=True)
                 ev_h2d[k].record(st_h2d)
+
+        def compute_and_d2h_of(i):
+            k = i % N_BUFFER_SETS
+            o = out_host[k]
             with torch.cuda.stream(st_cmp):
                 st_cmp.wait_event(ev_h2d[k])
                 st_cmp.wait_event(ev_d2h[k])          # the previous results of this set have left the device
@@ -588,17 +592,25 @@ def run_native_arm(args):
                 o["fg"].copy_(fg, non_blocking=True)
                 ev_d2h[k].record(st_d2h)
 
+        def pipeline(first, count):
+            """`count` steps, every one with its H2D, compute and D2H issued here; the inputs of step i+1 are put on
+            the copy stream BEFORE step i is issued (a data loader's prefetch of depth 1), so a step whose host code
+            has to wait for the device (the API sequence reads two counts back) does not hold up the next upload."""
+            h2d_of(first)
+            for i in range(first, first + count):
+                if i + 1 < first + count:
+                    h2d_of(i + 1)
+                compute_and_d2h_of(i)
+
         def run(steps, warmup):
-            for i in range(warmup):
-                e2e_step(i)
+            pipeline(0, warmup)
             ctx.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             cur = torch.cuda.current_stream()
             e0.record(cur)
             for stream in (st_h2d, st_cmp, st_d2h):
                 stream.wait_event(e0)
-            for i in range(steps):
-                e2e_step(warmup + i)
+            pipeline(warmup, steps)
             for stream in (st_h2d, st_cmp, st_d2h):
                 cur.wait_stream(stream)
             e1.record(cur)

@@ -5,7 +5,7 @@
  * sizes (no torch types), launches hand-written CUDA kernels asynchronously on the
  * stream the caller passes (a cudaStream_t cast to void*; NULL = legacy default
  * stream) and returns 0 or a negative bevpool_status / positive cudaError_t.
- * Nothing here synchronises the device (bevpool_prepare_v2_counts alone waits for one 8-byte copy) and nothing
+ * Nothing here synchronises the device (bevpool_prepare_v2_counts alone waits, for two integers) and nothing
  * falls back to the CPU.
  *
  * Reference interfaces replaced (paths relative to
@@ -132,9 +132,9 @@ int bevpool_prepare_v2(const float* coor, const float* frustum, const float* rot
 /* Same work, plus the two counts handed back to the HOST (host_counts[0] = P, host_counts[1] = I) — what the
  * reference API needs to return exact-length tensors (cam_stream_lss_bevpoolv2.py:324-351 reads them through
  * boolean-mask indexing and torch.where). P is final after the rank kernel and I equals the number of occupied
- * voxels (a bitmap filled by the same kernel), so the 8-byte copy is queued BEFORE the sort and the segmentation:
- * the call returns as soon as that copy has landed, with the remaining kernels still running on `stream`.
- * This is the only entry point that waits for the device; it refuses a capturing stream (BEVPOOL_ERR_BAD_ARG). */
+ * voxels (a bitmap filled by the same kernel), so a small kernel stores both into page-locked host memory BEFORE the sort
+ * and the segmentation: the call returns as soon as that kernel is done, with the remaining kernels still running on
+ * `stream`. This is the only entry point that waits for the device; it refuses a capturing stream (BEVPOOL_ERR_BAD_ARG). */
 int bevpool_prepare_v2_counts(const float* coor, const float* frustum, const float* rots, const float* trans,
                               const bevpool_grid_t* g,
                               int32_t* ranks_bev, int32_t* ranks_depth, int32_t* ranks_feat,

@@ -58,7 +58,7 @@ CountSlot* acquire_count_slot() {
   CountSlot* s = new CountSlot;
   s->dev = dev;
   s->host = nullptr;
-  if (cudaHostAlloc((void**)&s->host, 2 * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess ||
+  if (cudaHostAlloc((void**)&s->host, 2 * sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
       cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming) != cudaSuccess) {
     if (s->host) cudaFreeHost(s->host);
     delete s;

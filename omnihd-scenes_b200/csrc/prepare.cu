@@ -229,9 +229,12 @@ key_hist_kernel(const int* __restrict__ keys, int64_t n, SortPlan plan, uint32_t
 
 // Early counts for the host (bevpool_prepare_v2_counts): P is final once the rank kernel is done, and the number
 // of intervals equals the number of occupied voxels — no need to wait for the sort and the segmentation.
+// The last CTA to finish stores both straight into page-locked host memory (no copy-engine transfer: an 8-byte
+// cudaMemcpyAsync would queue behind whatever bulk device->host copy another stream has in flight).
 __global__ void __launch_bounds__(256)
 early_counts_kernel(const uint32_t* __restrict__ occupied, int64_t words, const int* __restrict__ n_kept,
-                    int* __restrict__ early /*[2], zeroed*/) {
+                    int* __restrict__ early /*[0] = occupied voxels, [1] = finished CTAs; zeroed*/,
+                    volatile int32_t* __restrict__ host_counts /*[2], mapped pinned*/) {
   pdl_wait();
   __shared__ uint32_t s_sum;
   if (threadIdx.x == 0) s_sum = 0;
@@ -243,8 +246,14 @@ early_counts_kernel(const uint32_t* __restrict__ occupied, int64_t words, const 
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_sum, mine);
   __syncthreads();
   if (threadIdx.x == 0) {
-    if (s_sum) atomicAdd(early + 1, (int)s_sum);
-    if (blockIdx.x == 0) early[0] = *n_kept;
+    if (s_sum) atomicAdd(early, (int)s_sum);
+    __threadfence();
+    if (atomicAdd(early + 1, 1) == (int)gridDim.x - 1) {
+      __threadfence();
+      host_counts[0] = *n_kept;
+      host_counts[1] = *(volatile int*)early;
+      __threadfence_system();
+    }
   }
 }
 
@@ -672,13 +681,12 @@ static int prepare_impl(const float* coor, const float* frustum, const float* ro
   }
   count_launch();
   if (slot) {
-    // counts leave for the host now; everything below is queued behind them and the host waits for the copy only
+    // counts leave for the host now; everything below is queued behind them and the host waits for this kernel only
     const int64_t words = (v + 31) / 32;
     int eb = (int)((words + 255) / 256);
     if (eb > kNumSMs * 4) eb = kNumSMs * 4;
-    early_counts_kernel<<<eb, 256, 0, st>>>(occupied, words, counts_dev, early);
+    early_counts_kernel<<<eb, 256, 0, st>>>(occupied, words, counts_dev, early, slot->host);
     count_launch();
-    cudaMemcpyAsync(slot->host, early, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
     cudaEventRecord(slot->ev, st);
   }
 
