@@ -354,6 +354,19 @@ def reference_gpu_variants(ctx, pkg, cfg, sets, steps):
         "note": "unmodified reference LiftSplatShoot.get_voxels after plugin.install() + patch_lss_class(): same kernels "
                 "as the headline, eager launches (no CUDA graph)"}
     pkg.plugin.unpatch_lss_class(ref.LiftSplatShoot)
+    # ---- (a') the same class with patch_lss_class(cuda_graph=True): get_voxels replays graphs of the fused transform
+    #      (inputs are copied into the graphs' static buffers every call: rotating buffer sets never match them)
+    try:
+        pkg.plugin.patch_lss_class(ref.LiftSplatShoot, cuda_graph=True)
+        ms = ctx.timed(zero_edit, n, EAGER_WARMUP)
+        out["reference_class_zero_edit_graphed"] = {
+            "value": ctx.world * B * n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / n,
+            "note": "as reference_class_zero_edit with patch_lss_class(cuda_graph=True): torch.cuda.make_graphed_callables "
+                    "over the fused view transform, autograd intact; includes the copies into / out of static buffers"}
+    except Exception as ex:
+        out["reference_class_zero_edit_graphed"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+    pkg.plugin.unpatch_lss_class(ref.LiftSplatShoot)
+    lss.__dict__.pop("_bevpool_b200_graphs", None)
 
     # ---- (b) the reference's own extension + torch-op prepare
     if ref_ext.available():

@@ -73,9 +73,27 @@ def fused_view_of(lss):
     return view
 
 
-def patch_lss_class(cls, fused=True):
+def _graphed_view_of(lss, depth, feat, rots, trans):
+    """Per-signature cache of CUDA-graphed forms of `fused_view_of(lss)` (LSSViewTransform.graphed)."""
+    view = fused_view_of(lss)
+    import torch
+    key = (tuple(depth.shape), tuple(feat.shape), depth.dtype, feat.dtype, depth.requires_grad, feat.requires_grad,
+           torch.is_grad_enabled(), id(view))
+    cache = lss.__dict__.setdefault("_bevpool_b200_graphs", {})
+    fn = cache.get(key)
+    if fn is None:
+        if len(cache) >= 8:
+            cache.clear()
+        fn = cache[key] = view.graphed(depth, feat, rots, trans)
+    return fn
+
+
+def patch_lss_class(cls, fused=True, cuda_graph=False):
     """Swap the view-transform methods of a reference LSS class for the CUDA-backed ones (see module docstring).
-    fused=False keeps the reference's own `get_voxels` (geometry -> prepare -> bev_pool_v2 call sequence)."""
+    fused=False keeps the reference's own `get_voxels` (geometry -> prepare -> bev_pool_v2 call sequence).
+    cuda_graph=True (opt-in, fixed shapes): `get_voxels` replays a CUDA graph of the fused view transform, forward and
+    backward (one pair per input signature) — the step's launches and Python glue disappear; the returned BEV grid
+    lives in a static buffer that the next call overwrites."""
 
     def voxel_pooling_prepare_v2(self, coor):
         return _vt.voxel_pooling_prepare_v2(coor, self.dx, self.bx, self.nx)
@@ -96,12 +114,16 @@ def patch_lss_class(cls, fused=True):
         feat, depth = self.get_cam_feats(x)
         if feat.shape[2] % 4:      # channel counts the fused kernels do not take: the reference's own sequence
             return self.voxel_pooling_v2(self.get_geometry(rots, trans), depth, feat), depth
-        return fused_view_of(self)(depth, feat, rots.float(), trans.float()), depth
+        rots, trans = rots.float(), trans.float()
+        if cls._bevpool_b200_cuda_graph and depth.is_cuda:
+            return _graphed_view_of(self, depth, feat, rots, trans)(depth, feat, rots, trans), depth
+        return fused_view_of(self)(depth, feat, rots, trans), depth
 
     if not hasattr(cls, "_bevpool_b200_orig_get_geometry"):
         cls._bevpool_b200_orig_get_geometry = cls.get_geometry
         cls._bevpool_b200_orig_prepare = cls.voxel_pooling_prepare_v2
         cls._bevpool_b200_orig_get_voxels = getattr(cls, "get_voxels", None)
+    cls._bevpool_b200_cuda_graph = bool(cuda_graph)
     cls.voxel_pooling_prepare_v2 = voxel_pooling_prepare_v2
     cls.get_geometry = get_geometry
     if fused and cls._bevpool_b200_orig_get_voxels is not None:
@@ -126,6 +148,8 @@ def unpatch_lss_class(cls):
         if cls._bevpool_b200_orig_get_voxels is not None:
             cls.get_voxels = cls._bevpool_b200_orig_get_voxels
         del cls._bevpool_b200_orig_get_geometry, cls._bevpool_b200_orig_prepare, cls._bevpool_b200_orig_get_voxels
+        if hasattr(cls, "_bevpool_b200_cuda_graph"):
+            del cls._bevpool_b200_cuda_graph
     mod = sys.modules.get(cls.__module__)
     if mod is not None and hasattr(mod, "_bevpool_b200_orig_bev_pool_v2"):
         mod.bev_pool_v2 = mod._bevpool_b200_orig_bev_pool_v2

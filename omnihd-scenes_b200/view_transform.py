@@ -351,6 +351,29 @@ class _FusedViewPool(torch.autograd.Function):
         return depth_grad, feat_grad, None, None, None, None, None, None
 
 
+class _GraphedForward:
+    """Forward-only CUDA graph of a view transform over static input copies (LSSViewTransform.graphed without grads)."""
+
+    def __init__(self, view, sample):
+        self.static_in = [t.detach() for t in sample]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(3):
+                view(*self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.out = view(*self.static_in)
+
+    def __call__(self, depth, feat, rots, trans):
+        for s, t in zip(self.static_in, (depth, feat, rots, trans)):
+            if s.data_ptr() != t.data_ptr():
+                s.copy_(t)
+        self.graph.replay()
+        return self.out
+
+
 class LSSViewTransform(nn.Module):
     """View-transform part of the reference's `LiftSplatShoot` (cam_stream_lss_bevpoolv2.py:149-375):
     same attribute names (`dx`, `bx`, `nx`, `frustum`, `D`, `fH`, `fW`) and method names, no conv nets.
@@ -464,6 +487,19 @@ class LSSViewTransform(nn.Module):
                 raise ValueError("s2c and channels_last_3d are exclusive (s2c of a channels-last grid is not a view)")
             s2c = "channels_last"
         return _FusedViewPool.apply(depth, feat, rots, trans, self, groups, feat_channels_last, s2c)
+
+    def graphed(self, depth, feat, rots, trans):
+        """CUDA-graphed form of `forward` for fixed shapes (training or inference loops): the ~12 launches of a step
+        and their Python become two graph replays (forward, backward). Built with `torch.cuda.make_graphed_callables`
+        on sample tensors of the real shapes / dtypes / requires_grad flags; the returned callable takes
+        `(depth, feat, rots, trans)` and is differentiable. The usual CUDA-graph contract applies: outputs (and input
+        gradients) live in static buffers that the NEXT call overwrites — consume or clone them before calling again.
+        Nothing in the fused path synchronises with the host, which is what makes it capturable."""
+        sample = tuple(t.detach().clone().requires_grad_(t.requires_grad) for t in (depth, feat, rots, trans))
+        if torch.is_grad_enabled() and any(t.requires_grad for t in sample):
+            # a plain function, not `self`: for a Module make_graphed_callables swaps `forward` in place
+            return torch.cuda.make_graphed_callables(lambda d, f, r, t: self.forward(d, f, r, t), sample)
+        return _GraphedForward(self, sample)          # inference: nothing to differentiate, one forward graph
 
     def lift_splat(self, x, rots, trans, C, s2c=False):
         """Depthnet output x [B*N, D+C, fH, fW] -> BEV grid [B,C,Z,Y,X]: fused softmax/split/transpose head

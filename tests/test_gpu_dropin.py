@@ -131,6 +131,55 @@ def test_unmodified_reference_lss_with_patched_methods(pkg, orc, refimport, case
     _cleanup(refimport)
 
 
+def test_unmodified_reference_lss_cuda_graphed(pkg, orc, refimport):
+    """patch_lss_class(cls, cuda_graph=True): the unmodified LiftSplatShoot.get_voxels replays a CUDA graph of the fused
+    view transform (forward and backward). Several steps with fresh inputs through the SAME graphs vs the float64 oracle
+    and vs the eager fused route (gradients are bit-identical; the forward sums meet in L2 atomics, so 1e-5)."""
+    _cleanup(refimport)
+    pkg.plugin.install(force=True)
+    ref = refimport.import_reference_lss("bevfusion")
+    torch.manual_seed(1)
+    case = CASE
+    lss = refimport.make_reference_lss(ref, case["final_dim"], case["downsample"], case["dbound"], case["xb"], case["yb"],
+                                       case["zb"], inputC=8, camC=8).to(DEV)
+    B, N, C = 2, 6, 8
+    X, Y, Z = (int(v) for v in lss.nx)
+    cur = {}
+    lss.__dict__["get_cam_feats"] = lambda x: (cur["feat"], cur["depth"])       # the conv nets are out of scope here
+    results = {}
+    for mode in ("eager", "graph"):
+        pkg.plugin.patch_lss_class(ref.LiftSplatShoot, cuda_graph=(mode == "graph"))
+        out = []
+        for step in range(3):
+            g = torch.Generator().manual_seed(100 + step)
+            rots, trans = pkg.synthetic.camera_ring(B, N, case["final_dim"], seed=20 + step)
+            depth = torch.rand(B, N, lss.D, lss.fH, lss.fW, generator=g).softmax(2).to(DEV).requires_grad_()
+            feat = torch.randn(B, N, C, lss.fH, lss.fW, generator=g).to(DEV).requires_grad_()
+            gout = torch.randn(B, C, Z, Y, X, generator=g).to(DEV)
+            cur["feat"], cur["depth"] = feat, depth
+            bev, d_out = lss.get_voxels(None, rots.to(DEV), trans.to(DEV))
+            assert d_out is depth and bev.shape == (B, C, Z, Y, X)
+            bev.backward(gout)
+            out.append((bev.detach().clone(), depth.grad.clone(), feat.grad.clone()))
+            if mode == "graph" and step == 2:
+                _, _, want, gd, gf = _oracle_case(orc, lss, rots, trans, depth.detach().cpu().numpy(),
+                                                  feat.detach().cpu().numpy(), gout.cpu().numpy())
+                assert rel_to_max(out[-1][0].permute(0, 2, 3, 4, 1).cpu().numpy(), want) <= TOL
+                assert rel_to_max(out[-1][1].cpu().numpy(), gd) <= TOL and rel_to_max(out[-1][2].cpu().numpy(), gf) <= TOL
+        results[mode] = out
+        if mode == "graph":
+            assert len(lss.__dict__["_bevpool_b200_graphs"]) == 1           # one graph pair served all three steps
+            with torch.no_grad():                                           # inference signature: its own graph
+                cur["feat"], cur["depth"] = feat.detach(), depth.detach()
+                bev_ng, _ = lss.get_voxels(None, rots.to(DEV), trans.to(DEV))
+            assert rel_to_max(bev_ng.cpu().numpy(), out[-1][0].cpu().numpy()) <= TOL
+        pkg.plugin.unpatch_lss_class(ref.LiftSplatShoot)
+    for e, g in zip(results["eager"], results["graph"]):
+        assert rel_to_max(g[0].cpu().numpy(), e[0].cpu().numpy()) <= TOL
+        assert torch.equal(g[1], e[1]) and torch.equal(g[2], e[2])
+    _cleanup(refimport)
+
+
 @pytest.mark.parametrize("variant", ["rcfusion_depth", "bevfusion_depth"])
 def test_unmodified_depthnet_variants_voxel_pooling(pkg, orc, refimport, variant):
     """LiftSplatShoot_Depth (…_depthnet.py:269-350, both copies) cannot be CONSTRUCTED without mmcv (DCN, build_norm_layer),
