@@ -40,6 +40,7 @@ constexpr int kCgWarps = kCgW;              // warp = column
 constexpr int kCgThreads = kCgWarps * 32;
 constexpr int kCgChunk = 8;                 // items per stage of the out_grad row ring (a multiple of 2)
 constexpr int kCgStages = 2;
+constexpr int kCgInFlight = 4;   // depth bins per warp whose loads are in flight while staging (8: no change, measured)
 
 struct ColParams {
   int d, h, w;
@@ -193,11 +194,11 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
   //      voxel and 0 otherwise, so the main loop needs no masking.
   {
     const bool w_in = w0 + wl < prm.w;
-    for (int d0 = warp; d0 < d_pad; d0 += 4 * kCgWarps) {
-      int r[4][4];
-      float dv[4][4];
+    for (int d0 = warp; d0 < d_pad; d0 += kCgInFlight * kCgWarps) {
+      int r[kCgInFlight][4];
+      float dv[kCgInFlight][4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kCgInFlight; ++u) {
         const int d = d0 + u * kCgWarps;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -212,7 +213,7 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kCgInFlight; ++u) {
         const int d = d0 + u * kCgWarps;
         // kept rows of column wl as a 16-bit mask: ballot k holds rows 4k + hl at bit 8 hl + wl; 0x10204080 gathers the
         // four bits 0, 8, 16, 24 of a word into its top nibble
