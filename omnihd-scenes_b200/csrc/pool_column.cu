@@ -42,6 +42,18 @@ constexpr int kCgChunk = 8;                 // items per stage of the out_grad r
 constexpr int kCgStages = 2;
 constexpr int kCgInFlight = 4;   // depth bins per warp whose loads are in flight while staging (8: no change, measured)
 
+#ifdef BEVPOOL_TIMELINE   // measurement builds only (profiles/timeline_col.py): per-CTA phase stamps in ns
+__device__ unsigned long long g_col_timeline[8 * 4096];
+__device__ __forceinline__ unsigned long long col_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define COL_STAMP(k) do { if (threadIdx.x == 0) tl[k] = col_now(); } while (0)
+#else
+#define COL_STAMP(k) do { } while (0)
+#endif
+
 struct ColParams {
   int d, h, w;
   int feat_grad_nchw;
@@ -185,6 +197,10 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
   const int hw = prm.h * prm.w;
   const int64_t img_base = (int64_t)bn * prm.d * hw;
   pdl_wait();
+#ifdef BEVPOOL_TIMELINE
+  unsigned long long tl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+  COL_STAMP(0);
   if (threadIdx.x < kCgW * kCgStages) mbar_init(s_full + threadIdx.x, 1);
 
   // ---- stage the depth WEIGHTS of the tile and reduce the ranks to per-(column, bin) summaries. A warp takes bins
@@ -256,6 +272,7 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
   // make the barrier initialisation visible to the async proxy before any bulk copy names it
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
+  COL_STAMP(1);
 
   const int ww = w0 + warp;                 // this warp's image column
   const int rg = lane >> 3, cg = lane & 7;  // row group (rows 4rg .. 4rg + 3), channel group
@@ -312,10 +329,17 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
 
     const int n_chunks = (n_items + kCgChunk - 1) / kCgChunk;
     if (n_chunks > 0) issue(0, 0);
+    COL_STAMP(2);
+#ifdef BEVPOOL_TIMELINE
+    if (threadIdx.x == 0) tl[7] = ((unsigned long long)n_items << 16) | ((unsigned long long)any_more << 15);
+#endif
     for (int ch = 0; ch < n_chunks; ++ch) {
       const int stage = ch & 1;
       if (ch + 1 < n_chunks) issue(ch + 1, stage ^ 1);
       mbar_wait(full + stage, (uint32_t)(ch >> 1) & 1u);
+#ifdef BEVPOOL_TIMELINE
+      if (ch == 0) COL_STAMP(3);
+#endif
       const int j0 = ch * kCgChunk;
       const int np = min(kCgChunk, n_items - j0) >> 1;   // full pairs of this chunk; an odd last item is done after the loop
       const T* rows = ring + (size_t)stage * kCgChunk * C;
@@ -374,7 +398,9 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
       }
     }
   }
+  COL_STAMP(4);
   __syncthreads();   // all warps are done with s_depth and the rings: the feat_grad tile may overwrite them
+  COL_STAMP(5);
 
   // ---- feat_grad of the 16 x 8 pixels
   if (prm.feat_grad_nchw) {
@@ -416,6 +442,19 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
         if (K2) RowIO<T>::st2(o + 32 * K4 + 2 * cg, fg[p].t);
       }
   }
+#ifdef BEVPOOL_TIMELINE
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int slot = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (slot < 4096) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      tl[6] = col_now();
+      tl[7] |= smid;
+      for (int k = 0; k < 8; ++k) g_col_timeline[8 * slot + k] = tl[k];
+    }
+  }
+#endif
 }
 
 template <typename T, int K4, bool K2>
@@ -478,3 +517,10 @@ int backward_column(const void* og, void* dg, void* fg, const void* depth, const
 }
 
 }  // namespace bevpool
+
+#ifdef BEVPOOL_TIMELINE
+extern "C" int bevpool_debug_col_timeline(unsigned long long* host_out, int n) {
+  cudaMemcpyFromSymbol(host_out, bevpool::g_col_timeline, sizeof(unsigned long long) * 8 * (n < 4096 ? n : 4096));
+  return (int)cudaGetLastError();
+}
+#endif

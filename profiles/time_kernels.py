@@ -7,7 +7,7 @@ pkg = load_package()
 lib = pkg._lib.load()
 cfg = pkg.synthetic.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "bevdet_r50_b8"]
 B = int(sys.argv[2]) if len(sys.argv) > 2 else cfg.batch
-NS = 4
+NS = int(os.environ.get("NS", 4))
 dev = torch.device("cuda:0")
 bp = pkg.bev_pool
 view = pkg.LSSViewTransform.from_config(cfg).to(dev)
