@@ -30,17 +30,19 @@
 // finished on a slow path, one extra item per additional voxel, with the row loaded straight into registers: results
 // are exact on any grid, only the speed differs. Z > 1 grids keep the block kernels (pool_dense.cu): there an item is
 // barely longer than a point and the dense 16-row products would be wasted.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace bevpool {
 
 constexpr int kCgRows = 16;                 // image rows per column tile
-constexpr int kCgW = 8;                     // columns per CTA: 8 consecutive w = one 32-byte sector per (d, h)
-constexpr int kCgWarps = kCgW;              // warp = column
-constexpr int kCgThreads = kCgWarps * 32;
+// Columns per CTA (template parameter WL of the kernel; warp = column, WL * 32 threads): 8 consecutive w = one 32-byte
+// sector of depth / point_rank per (d, h), two CTAs per SM; or 16 = 64 bytes per (d, h), one 16-warp CTA per SM. The
+// staging phase and the write-outs are bound by L1 wavefronts (one per distinct 128-byte line a warp access touches,
+// profiles/r2_ncu_bwd_column.md): 16-column tiles halve them.
 constexpr int kCgChunk = 8;                 // items per stage of the out_grad row ring (a multiple of 2)
 constexpr int kCgStages = 2;
-constexpr int kCgInFlight = 4;   // depth bins per warp whose loads are in flight while staging (8: no change, measured)
 
 #ifdef BEVPOOL_TIMELINE   // measurement builds only (profiles/timeline_col.py): per-CTA phase stamps in ns
 __device__ unsigned long long g_col_timeline[8 * 4096];
@@ -170,29 +172,38 @@ __device__ __forceinline__ float reduce_pair(const float (&a)[4], const float (&
   return (h1 ? k1 : k0) + __shfl_xor_sync(kFullMask, h1 ? k0 : k1, 1);
 }
 
-template <typename T, int K4, bool K2>
-__global__ void __launch_bounds__(kCgThreads, 2)
+template <typename T, int K4, bool K2, int WL, bool WIDE>
+__global__ void __launch_bounds__(WL * 32, 16 / WL)
 pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, const T* __restrict__ feat,
                        const int* __restrict__ point_rank, ColParams prm, T* __restrict__ depth_grad,
                        T* __restrict__ feat_grad) {
   constexpr int C = 32 * K4 + (K2 ? 16 : 0);
   constexpr uint32_t kRowBytes = C * sizeof(T);
+  constexpr int kCgW = WL, kCgWarps = WL;
+  constexpr int HL = 32 / WL;             // rows covered by one warp-wide staging access (4 or 2)
+  constexpr int KS = kCgRows / HL;        // row slots per thread while staging (4 or 8)
+  constexpr int kBins = 16 / KS;          // depth bins per warp in flight while staging: 32 loads per thread either way
+  constexpr unsigned kColBits = WL == 8 ? 0x01010101u : 0x00010001u;   // bit of column 0 in every row of a ballot
   using Sl = Slice<K4, K2>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int d_pad = (prm.d + 7) & ~7;
   const int CS = d_pad * kCgRows + 4;       // column stride of the [w][d][16] arrays: (4 w + h) mod 32 distinct per warp access
   float* s_depth = reinterpret_cast<float*>(smem_raw);                                // [8][CS] lead-masked depth weights
-  T* s_R = reinterpret_cast<T*>(s_depth + kCgW * CS);                                // [8 columns][stages][chunk][C]
-  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_R + kCgW * kCgStages * kCgChunk * C);   // [8][stages] rows have landed
-  int* s_lead = reinterpret_cast<int*>(s_full + kCgW * kCgStages);                   // [8][d_pad] lead rank, -1 = empty bin
-  int* s_items = s_lead + kCgW * d_pad;   // [8][d_pad]: per-bin summary (row mask | more << 16), later compacted in place to
+  T* s_R = reinterpret_cast<T*>(s_depth + kCgW * CS);                                // [WL columns][stages][chunk][C]
+  // (wide staging parks the raw ranks, [WL][CS] ints, in the ring's place: the region is the larger of the two)
+  constexpr size_t kRingBytes = sizeof(T) * kCgW * kCgStages * kCgChunk * C;
+  const size_t ring_region = WIDE ? (kRingBytes > sizeof(int) * kCgW * (size_t)CS ? kRingBytes : sizeof(int) * kCgW * (size_t)CS)
+                                  : kRingBytes;
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_R) + ring_region);   // [WL][stages]
+  int* s_lead = reinterpret_cast<int*>(s_full + kCgW * kCgStages);                   // [WL][d_pad] lead rank, -1 = empty bin
+  int* s_items = s_lead + kCgW * d_pad;   // [WL][d_pad]: per-bin summary (row mask | more << 16), later compacted in place to
                                           // the kept bins: bin | row mask << 8 | more << 24
   float* s_tile = s_depth;                // epilogue: [C][129] feat_grad transpose (over s_depth and the rings)
   // depth_grad goes straight to global memory: zeros for dropped points while staging, one 4-byte store per kept point from
   // the lane that holds its dot product (no shared-memory copy of the tile's gradients: half the footprint, D = 118 fits)
 
   const int lane = lane_id(), warp = threadIdx.x >> 5;
-  const int hl = lane >> 3, wl = lane & 7;
+  const int hl = lane / WL, wl = lane % WL;
   const int h0 = blockIdx.y * kCgRows, w0 = blockIdx.x * kCgW, bn = blockIdx.z;
   const int hw = prm.h * prm.w;
   const int64_t img_base = (int64_t)bn * prm.d * hw;
@@ -208,17 +219,122 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
   //      per pass. Summary of a (column, bin): lead = rank of its first kept row, row mask of the rows in that voxel,
   //      "more" if kept rows sit in other voxels too. The staged weight of a row is its depth if it belongs to the lead
   //      voxel and 0 otherwise, so the main loop needs no masking.
-  {
-    const bool w_in = w0 + wl < prm.w;
-    for (int d0 = warp; d0 < d_pad; d0 += kCgInFlight * kCgWarps) {
-      int r[kCgInFlight][4];
-      float dv[kCgInFlight][4];
+  if constexpr (WIDE) {
+    // ---- 16-column tiles, W % 4 == 0. A lane takes 4 consecutive columns of one row with 128-bit loads; a warp-wide access
+    //      covers rows row8 (+8) of all 16 columns of one depth bin, so the warp that loaded a bin holds all of its 256
+    //      values. They go to shared memory as they are (ranks into s_rank, which aliases the not yet used row ring; depth
+    //      into its final place) and then ONE LANE per (column, bin) reduces the 16 ranks of its pair to the summary and
+    //      masks the weights in place: ~150 instructions per pair and lane instead of ~100 ballot / shuffle instructions per
+    //      pair and WARP (the ballot form spent 3.7 M of the kernel's 17.4 M warp instructions here, r2_col_e capture).
+    static_assert(!WIDE || WL == 16, "wide staging is written for 16-column tiles");
+    constexpr int kBinsW = 4;   // depth bins per warp in flight: 16 128-bit loads per thread
+    int* s_rank = reinterpret_cast<int*>(s_R);   // [16][CS] raw ranks, dead before the first bulk copy is issued
+    const int row8 = lane >> 2, g = lane & 3;
+    const int wq = w0 + 4 * g;
+    const bool q_in = wq < prm.w;
+    for (int d0 = warp; d0 < d_pad; d0 += kBinsW * kCgWarps) {
+      int4 r[kBinsW][2];
+      float4 dv[kBinsW][2];
 #pragma unroll
-      for (int u = 0; u < kCgInFlight; ++u) {
+      for (int u = 0; u < kBinsW; ++u) {
         const int d = d0 + u * kCgWarps;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int h = h0 + 4 * k + hl;
+        for (int sl = 0; sl < 2; ++sl) {
+          const int h = h0 + 8 * sl + row8;
+          r[u][sl] = make_int4(-1, -1, -1, -1);
+          dv[u][sl] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (q_in && h < prm.h && d < prm.d) {
+            const int64_t o = img_base + (int64_t)d * hw + h * prm.w + wq;
+            r[u][sl] = ldg_stream_i32x4(point_rank + o);
+            dv[u][sl] = Vec4<T>::load_stream(depth, o);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBinsW; ++u) {
+        const int d = d0 + u * kCgWarps;
+        if (d >= d_pad) continue;   // warp-uniform
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int4 q = r[u][sl];
+          const float4 v = dv[u][sl];
+          // zeros for dropped points (nobody else writes them): one 16-byte store if all 4 are
+          const int h = h0 + 8 * sl + row8;
+          if (q_in && h < prm.h && d < prm.d) {
+            const int64_t o = img_base + (int64_t)d * hw + h * prm.w + wq;
+            if ((q.x & q.y & q.z & q.w) < 0) {
+              Vec4<T>::store(depth_grad, o, make_float4(0.f, 0.f, 0.f, 0.f));
+            } else {
+              if (q.x < 0) Vec4<T>::store1s(depth_grad, o + 0, 0.f);
+              if (q.y < 0) Vec4<T>::store1s(depth_grad, o + 1, 0.f);
+              if (q.z < 0) Vec4<T>::store1s(depth_grad, o + 2, 0.f);
+              if (q.w < 0) Vec4<T>::store1s(depth_grad, o + 3, 0.f);
+            }
+          }
+          const int e = (4 * g) * CS + d * kCgRows + 8 * sl + row8;   // column 4g, this row
+          s_rank[e] = q.x, s_rank[e + CS] = q.y, s_rank[e + 2 * CS] = q.z, s_rank[e + 3 * CS] = q.w;
+          s_depth[e] = v.x, s_depth[e + CS] = v.y, s_depth[e + 2 * CS] = v.z, s_depth[e + 3 * CS] = v.w;
+        }
+      }
+      __syncwarp();
+      // one lane per (column, bin): lanes 0-15 take the columns of bin 2 pass, lanes 16-31 those of bin 2 pass + 1
+#pragma unroll
+      for (int pass = 0; pass < kBinsW / 2; ++pass) {
+        const int d = d0 + (2 * pass + (lane >> 4)) * kCgWarps;
+        const int col = lane & 15;
+        if (d < d_pad) {
+          const int4* pr4 = reinterpret_cast<const int4*>(s_rank + col * CS + d * kCgRows);
+          float4* pw4 = reinterpret_cast<float4*>(s_depth + col * CS + d * kCgRows);
+          int rk[16];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int4 t = pr4[q4];
+            rk[4 * q4] = t.x, rk[4 * q4 + 1] = t.y, rk[4 * q4 + 2] = t.z, rk[4 * q4 + 3] = t.w;
+          }
+          unsigned kept = 0, same = 0;
+          int lead = -1;
+#pragma unroll
+          for (int i2 = 15; i2 >= 0; --i2) {
+            kept |= (unsigned)(rk[i2] >= 0) << i2;
+            lead = rk[i2] >= 0 ? rk[i2] : lead;   // ends as the rank of the first kept row
+          }
+#pragma unroll
+          for (int i2 = 0; i2 < 16; ++i2) same |= (unsigned)(rk[i2] == lead) << i2;
+          same &= kept;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            float4 t = pw4[q4];
+            t.x = (same >> (4 * q4 + 0)) & 1u ? t.x : 0.f;
+            t.y = (same >> (4 * q4 + 1)) & 1u ? t.y : 0.f;
+            t.z = (same >> (4 * q4 + 2)) & 1u ? t.z : 0.f;
+            t.w = (same >> (4 * q4 + 3)) & 1u ? t.w : 0.f;
+            pw4[q4] = t;
+          }
+          s_lead[col * d_pad + d] = kept ? lead : -1;
+          s_items[col * d_pad + d] = (int)(same | (kept != same ? 1u << 16 : 0u));
+        }
+      }
+      __syncwarp();
+    }
+    // the ring that aliases s_rank is written next by the async proxy (bulk copies)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  } else
+  {
+    const bool w_in = w0 + wl < prm.w;
+    // rows HL*k .. HL*k + HL-1 of column wl out of a ballot: bit WL*hl' + wl per row hl'
+    auto rows_of = [&](unsigned ballot) -> unsigned {
+      const unsigned b = (ballot >> wl) & kColBits;
+      return WL == 8 ? (b * 0x10204080u) >> 28 : (b | (b >> 15)) & 3u;
+    };
+    for (int d0 = warp; d0 < d_pad; d0 += kBins * kCgWarps) {
+      int r[kBins][KS];
+      float dv[kBins][KS];
+#pragma unroll
+      for (int u = 0; u < kBins; ++u) {
+        const int d = d0 + u * kCgWarps;
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          const int h = h0 + HL * k + hl;
           r[u][k] = -1;
           dv[u][k] = 0.f;
           if (w_in && h < prm.h && d < prm.d) {
@@ -229,35 +345,31 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
         }
       }
 #pragma unroll
-      for (int u = 0; u < kCgInFlight; ++u) {
+      for (int u = 0; u < kBins; ++u) {
         const int d = d0 + u * kCgWarps;
-        // kept rows of column wl as a 16-bit mask: ballot k holds rows 4k + hl at bit 8 hl + wl; 0x10204080 gathers the
-        // four bits 0, 8, 16, 24 of a word into its top nibble
+        // kept rows of column wl as a 16-bit mask, and the rank of its first kept row (lower slots override)
         unsigned kept = 0;
         int lead = -1;
 #pragma unroll
-        for (int k = 3; k >= 0; --k) {
-          const unsigned b = (__ballot_sync(kFullMask, r[u][k] >= 0) >> wl) & 0x01010101u;
-          const unsigned k4 = (b * 0x10204080u) >> 28;                 // kept rows 4k .. 4k + 3 of column wl
-          // rank of the first kept row of this slot (row 4k + hl' sits in lane 8 hl' + wl); lower slots override
-          const int first = __shfl_sync(kFullMask, r[u][k], 8 * (k4 ? __ffs(k4) - 1 : 0) + wl);
-          lead = k4 ? first : lead;
-          kept |= k4 << (4 * k);
+        for (int k = KS - 1; k >= 0; --k) {
+          const unsigned kq = rows_of(__ballot_sync(kFullMask, r[u][k] >= 0));   // kept rows HL*k .. of column wl
+          // row HL*k + hl' sits in lane WL*hl' + wl
+          const int first = __shfl_sync(kFullMask, r[u][k], WL * (kq ? __ffs(kq) - 1 : 0) + wl);
+          lead = kq ? first : lead;
+          kept |= kq << (HL * k);
         }
         unsigned same = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const unsigned b = (__ballot_sync(kFullMask, r[u][k] >= 0 && r[u][k] == lead) >> wl) & 0x01010101u;
-          same |= ((b * 0x10204080u) >> 28) << (4 * k);
-        }
+        for (int k = 0; k < KS; ++k)
+          same |= rows_of(__ballot_sync(kFullMask, r[u][k] >= 0 && r[u][k] == lead)) << (HL * k);
         if (d < d_pad) {
           float* pd = s_depth + wl * CS + d * kCgRows + hl;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            pd[4 * k] = (r[u][k] >= 0 && r[u][k] == lead) ? dv[u][k] : 0.f;
-            // depth_grad of a dropped point is 0 and nobody else writes it: stored here, 8 consecutive w per (d, h);
+          for (int k = 0; k < KS; ++k) {
+            pd[HL * k] = (r[u][k] >= 0 && r[u][k] == lead) ? dv[u][k] : 0.f;
+            // depth_grad of a dropped point is 0 and nobody else writes it: stored here, WL consecutive w per (d, h);
             // every kept point is written exactly once by the item that owns it (main loop or slow path)
-            const int h = h0 + 4 * k + hl;
+            const int h = h0 + HL * k + hl;
             if (r[u][k] < 0 && w_in && h < prm.h && d < prm.d)
               Vec4<T>::store1s(depth_grad, img_base + (int64_t)d * hw + h * prm.w + w0 + wl, 0.f);
           }
@@ -404,7 +516,7 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
 
   // ---- feat_grad of the 16 x 8 pixels
   if (prm.feat_grad_nchw) {
-    constexpr int TS = kCgRows * kCgW + 1;   // 129: channel stride of the transpose tile [c][16 rows][8 w]
+    constexpr int TS = kCgRows * kCgW + 1;   // channel stride of the transpose tile [c][16 rows][WL w] (129 / 257)
     if (ww < prm.w) {
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
@@ -424,9 +536,9 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
     }
     __syncthreads();
     if (w0 + wl < prm.w) {
-      // 32-byte runs of 8 consecutive w; a warp-wide store covers 4 rows of one channel
-      for (int cr = warp; cr < C * 4; cr += kCgWarps) {
-        const int c = cr >> 2, trow = 4 * (cr & 3) + hl;
+      // runs of WL consecutive w; a warp-wide store covers HL rows of one channel
+      for (int cr = warp; cr < C * KS; cr += kCgWarps) {
+        const int c = cr / KS, trow = HL * (cr % KS) + hl;
         if (h0 + trow < prm.h)
           Vec4<T>::store1s(feat_grad, ((int64_t)bn * C + c) * hw + (h0 + trow) * prm.w + w0 + wl,
                            s_tile[c * TS + trow * kCgW + wl]);
@@ -457,28 +569,51 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
 #endif
 }
 
-template <typename T, int K4, bool K2>
-static int backward_column_launch(const void* og, void* dg, void* fg, const void* depth, const void* feat,
-                                  const int* point_rank, int bn, const ColParams& prm, cudaStream_t st) {
+template <typename T, int K4, bool K2, int WL, bool WIDE>
+static int backward_column_launch_w(const void* og, void* dg, void* fg, const void* depth, const void* feat,
+                                    const int* point_rank, int bn, const ColParams& prm, cudaStream_t st) {
   constexpr int C = 32 * K4 + (K2 ? 16 : 0);
   const size_t d_pad = (size_t)((prm.d + 7) & ~7);
-  const size_t col_bytes = sizeof(float) * kCgW * (d_pad * kCgRows + 4);
-  const size_t ring_bytes = sizeof(T) * kCgW * kCgStages * kCgChunk * C;
-  const size_t main_bytes = col_bytes + ring_bytes + sizeof(uint64_t) * kCgW * kCgStages + 2 * sizeof(int) * kCgW * d_pad;
-  const size_t tile_bytes = prm.feat_grad_nchw ? sizeof(float) * C * (kCgRows * kCgW + 1) : 0;
+  const size_t col_bytes = sizeof(float) * WL * (d_pad * kCgRows + 4);
+  size_t ring_bytes = sizeof(T) * WL * kCgStages * kCgChunk * C;
+  if (WIDE && ring_bytes < sizeof(int) * WL * (d_pad * kCgRows + 4)) ring_bytes = sizeof(int) * WL * (d_pad * kCgRows + 4);
+  const size_t main_bytes = col_bytes + ring_bytes + sizeof(uint64_t) * WL * kCgStages + 2 * sizeof(int) * WL * d_pad;
+  const size_t tile_bytes = prm.feat_grad_nchw ? sizeof(float) * C * (kCgRows * WL + 1) : 0;
   const size_t smem = main_bytes > tile_bytes ? main_bytes : tile_bytes;
-  // Two CTAs (16 warps) per SM are what keeps the FMA pipe fed. Measured dispatch rule: on deep frusta (cfg 3: D = 118,
-  // 32 x 88 features, 2 112 CTAs) the joint kernel is faster even when the tile fits twice per SM (bf16: 152 vs 169 us,
-  // fp32 at one CTA per SM: 146 vs 185-227 us), so tiles deeper than 64 bins stay with it (profiles/r2_ncu_bwd_column.md).
-  if (smem > 113 * 1024 || prm.d > 64) return BEVPOOL_ERR_BAD_ARG;
-  const int blocks_w = (prm.w + kCgW - 1) / kCgW, blocks_h = (prm.h + kCgRows - 1) / kCgRows;
+  // 16 warps per SM (two 8-column CTAs or one 16-column CTA) are what keeps the FMA pipe fed
+  if (smem > (size_t)(113 * 1024) * (WL / 8)) return BEVPOOL_ERR_BAD_ARG;
+  const int blocks_w = (prm.w + WL - 1) / WL, blocks_h = (prm.h + kCgRows - 1) / kCgRows;
   if (blocks_h > 65535 || bn > 65535) return BEVPOOL_ERR_OVERFLOW;
-  auto kern = pool_bwd_column_kernel<T, K4, K2>;
+  auto kern = pool_bwd_column_kernel<T, K4, K2, WL, WIDE>;
   if (int rc = ensure_dynamic_smem(kern, smem)) return rc;
-  launch_pdl(kern, dim3((unsigned)blocks_w, (unsigned)blocks_h, (unsigned)bn), dim3(kCgThreads), smem, st, (const T*)og,
+  launch_pdl(kern, dim3((unsigned)blocks_w, (unsigned)blocks_h, (unsigned)bn), dim3(WL * 32), smem, st, (const T*)og,
              (const T*)depth, (const T*)feat, point_rank, prm, (T*)dg, (T*)fg);
   count_launch();
   return launch_status();
+}
+
+template <typename T, int K4, bool K2>
+static int backward_column_launch(const void* og, void* dg, void* fg, const void* depth, const void* feat,
+                                  const int* point_rank, int bn, const ColParams& prm, cudaStream_t st) {
+  // Measured dispatch rule: on deep frusta (cfg 3: D = 118, 32 x 88 features) the joint kernel is faster even when the
+  // tile fits twice per SM (bf16: 152 vs 169 us), so tiles deeper than 64 bins stay with it (profiles/r2_ncu_cfg3.md).
+  if (prm.d > 64) return BEVPOOL_ERR_BAD_ARG;
+  // 16-column tiles (64-byte pieces of depth / point_rank / the gradients per (d, h): half the L1 wavefronts of staging
+  // and write-out) when they cover the image width as tightly as 8-column tiles do. BEVPOOL_BWD_TILE_W=8|16 overrides
+  // (measurement only).
+  static const int forced = [] {
+    const char* e = getenv("BEVPOOL_BWD_TILE_W");
+    return e ? atoi(e) : 0;
+  }();
+  // the 16-column kernel stages with 128-bit loads: 4 consecutive columns per lane need W % 4 == 0 and 16-byte aligned arrays
+  const bool can16 = prm.w % 4 == 0 && ((uintptr_t)point_rank % 16) == 0 && ((uintptr_t)depth % 16) == 0 &&
+                     ((uintptr_t)dg % 16) == 0;
+  const bool wide = can16 && (forced ? forced == 16 : (prm.w + 15) / 16 * 16 == (prm.w + 7) / 8 * 8);
+  if (wide) {
+    const int rc = backward_column_launch_w<T, K4, K2, 16, true>(og, dg, fg, depth, feat, point_rank, bn, prm, st);
+    if (rc != BEVPOOL_ERR_BAD_ARG) return rc;
+  }
+  return backward_column_launch_w<T, K4, K2, 8, false>(og, dg, fg, depth, feat, point_rank, bn, prm, st);
 }
 
 // Column-GEMM backward when there is an instantiation for the channel count and the tile fits shared memory.

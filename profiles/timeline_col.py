@@ -8,7 +8,7 @@ lib2 = ctypes.CDLL(pkg._lib.library_path())
 for i in range(6):
     bwd(i)
 torch.cuda.synchronize()
-n = 288
+n = int(os.environ.get("NCTA", 288))
 buf = np.zeros(8 * n, dtype=np.uint64)
 lib2.bevpool_debug_col_timeline(buf.ctypes.data_as(ctypes.POINTER(ctypes.c_ulonglong)), n)
 t = buf.reshape(n, 8).astype(np.int64)
