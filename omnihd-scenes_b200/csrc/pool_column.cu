@@ -59,6 +59,7 @@ __device__ __forceinline__ unsigned long long col_now() {
 struct ColParams {
   int d, h, w;
   int feat_grad_nchw;
+  int d_pad, cs, hw;   // (d + 7) & ~7; column stride d_pad * 16 + 4 of the [w][d][16] arrays; h * w (set by the launcher)
 };
 
 // ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ---------------------------------------------------
@@ -186,8 +187,8 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
   constexpr unsigned kColBits = WL == 8 ? 0x01010101u : 0x00010001u;   // bit of column 0 in every row of a ballot
   using Sl = Slice<K4, K2>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int d_pad = (prm.d + 7) & ~7;
-  const int CS = d_pad * kCgRows + 4;       // column stride of the [w][d][16] arrays: (4 w + h) mod 32 distinct per warp access
+  const int d_pad = prm.d_pad;
+  const int CS = prm.cs;                    // column stride of the [w][d][16] arrays: (4 w + h) mod 32 distinct per warp access
   float* s_depth = reinterpret_cast<float*>(smem_raw);                                // [8][CS] lead-masked depth weights
   T* s_R = reinterpret_cast<T*>(s_depth + kCgW * CS);                                // [WL columns][stages][chunk][C]
   // (wide staging parks the raw ranks, [WL][CS] ints, in the ring's place: the region is the larger of the two)
@@ -205,7 +206,7 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const int hl = lane / WL, wl = lane % WL;
   const int h0 = blockIdx.y * kCgRows, w0 = blockIdx.x * kCgW, bn = blockIdx.z;
-  const int hw = prm.h * prm.w;
+  const int hw = prm.hw;
   const int64_t img_base = (int64_t)bn * prm.d * hw;
   pdl_wait();
 #ifdef BEVPOOL_TIMELINE
@@ -401,7 +402,10 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
     const int* lead_col = s_lead + warp * d_pad;
     int* items = s_items + warp * d_pad;
     const float* depth_col = s_depth + warp * CS + 4 * rg;
-    T* dg_col = depth_grad + img_base + (int64_t)h0 * prm.w + ww;   // + bin * hw + row * W
+    // depth_grad of (bin, row) is addressed with ONE 32-bit offset from the tensor base (the launcher checks that the
+    // tensor has fewer than 2^31 elements): the address is rebuilt per store — no register survives the FMA block —
+    // and this form costs 3 instructions instead of a 64-bit multiply chain
+    T* dg_img = depth_grad;
     T* ring = s_R + (size_t)warp * kCgStages * kCgChunk * C;
     uint64_t* full = s_full + warp * kCgStages;
 
@@ -438,6 +442,7 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
       item_fma<K4, K2>(r, w, fv, fg, dot);
     };
     const int my_row = 4 * rg + (cg & 3);   // the row whose dot product this lane holds after reduce_pair
+    const int dg_lane = (int)img_base + (h0 + my_row) * prm.w + ww;
 
     const int n_chunks = (n_items + kCgChunk - 1) / kCgChunk;
     if (n_chunks > 0) issue(0, 0);
@@ -455,7 +460,7 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
       const int j0 = ch * kCgChunk;
       const int np = min(kCgChunk, n_items - j0) >> 1;   // full pairs of this chunk; an odd last item is done after the loop
       const T* rows = ring + (size_t)stage * kCgChunk * C;
-#pragma unroll
+#pragma unroll 1
       for (int pr = 0; pr < kCgChunk / 2; ++pr) {
         if (pr >= np) break;   // warp-uniform
         const int rec_a = items[j0 + 2 * pr], rec_b = items[j0 + 2 * pr + 1];
@@ -464,7 +469,7 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
         run_item(slice_load<T, K4, K2, false>(rows + (size_t)(2 * pr + 1) * C, cg), rec_b & 255, db);
         const float dot = reduce_pair(da, db, cg);
         const int mine = (cg & 4) ? rec_b : rec_a;
-        if ((mine >> (8 + my_row)) & 1) Vec4<T>::store1(dg_col, (int64_t)(mine & 255) * hw + my_row * prm.w, dot);
+        if ((mine >> (8 + my_row)) & 1) Vec4<T>::store1(dg_img, dg_lane + (mine & 255) * hw, dot);
       }
       __syncwarp();   // every lane is done with this stage before the next issue() refills it
     }
@@ -477,7 +482,7 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
       const float db[4] = {0.f, 0.f, 0.f, 0.f};
       run_item(slice_load<T, K4, K2, false>(rowp, cg), rec & 255, da);
       const float dot = reduce_pair(da, db, cg);
-      if (!(cg & 4) && ((rec >> (8 + my_row)) & 1)) Vec4<T>::store1(dg_col, (int64_t)(rec & 255) * hw + my_row * prm.w, dot);
+      if (!(cg & 4) && ((rec >> (8 + my_row)) & 1)) Vec4<T>::store1(dg_img, dg_lane + (rec & 255) * hw, dot);
     }
 
     // ---- slow path: bins whose kept rows sit in more than one voxel; one extra item per additional voxel, its
@@ -505,7 +510,7 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
                        : 0.f;
           item_fma<K4, K2>(slice_load<T, K4, K2, true>(og + (int64_t)rank * C, cg), w, fv, fg, da);
           const float dot = reduce_pair(da, db, cg);
-          if (!(cg & 4) && ((mask >> my_row) & 1)) Vec4<T>::store1(dg_col, (int64_t)bin * hw + my_row * prm.w, dot);
+          if (!(cg & 4) && ((mask >> my_row) & 1)) Vec4<T>::store1(dg_img, dg_lane + bin * hw, dot);
         }
       }
     }
@@ -625,8 +630,11 @@ int backward_column(const void* og, void* dg, void* fg, const void* depth, const
   prm.h = h;
   prm.w = w;
   prm.feat_grad_nchw = feat_grad_nchw;
+  prm.d_pad = (d + 7) & ~7;
+  prm.cs = prm.d_pad * kCgRows + 4;
+  prm.hw = h * w;
   *handled = true;
-  if (d > 248) {
+  if (d > 248 || (int64_t)bn * d * h * w >= INT32_MAX) {
     *handled = false;
     return 0;
   }
