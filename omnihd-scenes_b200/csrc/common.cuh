@@ -261,6 +261,14 @@ __device__ __forceinline__ void cam_point(const float* __restrict__ frustum, con
   z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cam[6], px), __fmul_rn(cam[7], py)), __fmul_rn(cam[8], pz)), cam[11]);
 }
 
+// Same arithmetic on frustum values that are already in registers (callers that issue all their loads first)
+__device__ __forceinline__ void cam_point_of(float u, float v, float dd, const float* cam, float& x, float& y, float& z) {
+  const float px = __fmul_rn(u, dd), py = __fmul_rn(v, dd), pz = dd;
+  x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cam[0], px), __fmul_rn(cam[1], py)), __fmul_rn(cam[2], pz)), cam[9]);
+  y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cam[3], px), __fmul_rn(cam[4], py)), __fmul_rn(cam[5], pz)), cam[10]);
+  z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cam[6], px), __fmul_rn(cam[7], py)), __fmul_rn(cam[8], pz)), cam[11]);
+}
+
 // Voxel index of one coordinate: trunc((c - lo) / dx) with the reference's IEEE fp32 subtract and DIVIDE, bit for bit.
 //   inv > 0 : dx is a power of two and inv = 1/dx exactly: the divide IS a multiply (both are the correctly rounded
 //             value of the same real number);

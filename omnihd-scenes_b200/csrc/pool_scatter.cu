@@ -112,25 +112,39 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
     for (int d0 = 0; d0 < prm.d; d0 += 4 * kScWarps * BPI) {
       int r[4];
       float dv[4];
+      float fu[4], fv[4], fd[4];
+      // all loads of the pass first (the geometry below branches — guard band, range tests — and loads do not move
+      // across branches: issued per bin they cost one memory round trip each, r1 capture: half of the kernel's samples)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int dd = d0 + (k * kScWarps + warp) * BPI + bs;
         r[k] = -1;
-        dv[k] = 0.f;
+        dv[k] = fu[k] = fv[k] = fd[k] = 0.f;
         if (in && dd < prm.d) {
           const int64_t o = (int64_t)dd * hw + pix;
           dv[k] = Vec4<T>::load1(depth, img_base + o);
           if (prm.from_geometry) {
+            fu[k] = __ldg(frustum + 3 * o + 0);
+            fv[k] = __ldg(frustum + 3 * o + 1);
+            fd[k] = __ldg(frustum + 3 * o + 2);
+          } else {
+            r[k] = ldg_stream_i32(point_rank + img_base + o);
+          }
+        }
+      }
+      if (prm.from_geometry) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int dd = d0 + (k * kScWarps + warp) * BPI + bs;
+          if (in && dd < prm.d) {
             float x, y, z;
-            cam_point(frustum, s_cam, o, x, y, z);
+            cam_point_of(fu[k], fv[k], fd[k], s_cam, x, y, z);
             int vx, vy, vz;
             const bool ok = voxel_index(x, prm.lo[0], prm.dx[0], prm.inv[0], prm.nx, vx) &
                             voxel_index(y, prm.lo[1], prm.dx[1], prm.inv[1], prm.ny, vy) &
                             voxel_index(z, prm.lo[2], prm.dx[2], prm.inv[2], prm.nz, vz);
             if (ok) r[k] = (int)(frame_base + ((int64_t)vz * prm.ny + vy) * prm.nx + vx);
-            point_rank[img_base + o] = r[k];
-          } else {
-            r[k] = ldg_stream_i32(point_rank + img_base + o);
+            point_rank[img_base + (int64_t)dd * hw + pix] = r[k];
           }
         }
       }
