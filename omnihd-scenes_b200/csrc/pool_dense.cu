@@ -610,16 +610,30 @@ pool_bwd_block_kernel(const T* __restrict__ og, const T* __restrict__ depth, con
     const int hh = h0 + (px >> 3), ww = w0 + (px & 7);
     const bool in = hh < prm.h && ww < prm.w;
     const int64_t o0 = img_base + (int64_t)hh * prm.w + ww;
-    for (int dd = threadIdx.x >> 5; dd < prm.d; dd += kBwdWarps) {
-      int r = -1;
-      float dv = 0.f;
-      if (in) {
-        r = ldg_stream_i32(point_rank + o0 + dd * hw);
-        if (r >= 0) dv = Vec4<T>::load1(depth, o0 + dd * hw);
+    // four bins per warp in flight, rank and depth loaded independently (one dependent pair per bin and iteration
+    // cost two memory round trips per bin: D / 8 * 2 serialized latencies per CTA)
+    for (int dd0 = threadIdx.x >> 5; dd0 < prm.d; dd0 += 4 * kBwdWarps) {
+      int r[4];
+      float dv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int dd = dd0 + k * kBwdWarps;
+        r[k] = -1;
+        dv[k] = 0.f;
+        if (in && dd < prm.d) {
+          r[k] = ldg_stream_i32(point_rank + o0 + dd * hw);
+          dv[k] = Vec4<T>::load1(depth, o0 + dd * hw);
+        }
       }
-      s_rank[dd * kPixBlock + px] = r;
-      s_depth[dd * kPixBlock + px] = dv;
-      s_dg[dd * kPixBlock + px] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int dd = dd0 + k * kBwdWarps;
+        if (dd < prm.d) {
+          s_rank[dd * kPixBlock + px] = r[k];
+          s_depth[dd * kPixBlock + px] = r[k] >= 0 ? dv[k] : 0.f;
+          s_dg[dd * kPixBlock + px] = 0.f;
+        }
+      }
     }
   }
   __syncthreads();
@@ -766,16 +780,30 @@ pool_bwd_block_half_kernel(const T* __restrict__ og, const T* __restrict__ depth
     const int hh = h0 + (px >> 3), ww = w0 + (px & 7);
     const bool in = hh < prm.h && ww < prm.w;
     const int64_t o0 = img_base + (int64_t)hh * prm.w + ww;
-    for (int dd = threadIdx.x >> 5; dd < prm.d; dd += kBwdWarps) {
-      int r = -1;
-      float dv = 0.f;
-      if (in) {
-        r = ldg_stream_i32(point_rank + o0 + dd * hw);
-        if (r >= 0) dv = Vec4<T>::load1(depth, o0 + dd * hw);
+    // four bins per warp in flight, rank and depth loaded independently (one dependent pair per bin and iteration
+    // cost two memory round trips per bin: D / 8 * 2 serialized latencies per CTA)
+    for (int dd0 = threadIdx.x >> 5; dd0 < prm.d; dd0 += 4 * kBwdWarps) {
+      int r[4];
+      float dv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int dd = dd0 + k * kBwdWarps;
+        r[k] = -1;
+        dv[k] = 0.f;
+        if (in && dd < prm.d) {
+          r[k] = ldg_stream_i32(point_rank + o0 + dd * hw);
+          dv[k] = Vec4<T>::load1(depth, o0 + dd * hw);
+        }
       }
-      s_rank[dd * kPixBlock + px] = r;
-      s_depth[dd * kPixBlock + px] = dv;
-      s_dg[dd * kPixBlock + px] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int dd = dd0 + k * kBwdWarps;
+        if (dd < prm.d) {
+          s_rank[dd * kPixBlock + px] = r[k];
+          s_depth[dd * kPixBlock + px] = r[k] >= 0 ? dv[k] : 0.f;
+          s_dg[dd * kPixBlock + px] = 0.f;
+        }
+      }
     }
   }
   __syncthreads();

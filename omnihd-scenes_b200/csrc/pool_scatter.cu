@@ -90,11 +90,11 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
   const int hw = prm.h * prm.w;
   const int64_t img_base = (int64_t)bn * prm.d * hw;
   pdl_wait();
-  if (prm.from_geometry) {
-    if (threadIdx.x < 12)
-      s_cam[threadIdx.x] = threadIdx.x < 9 ? __ldg(rots + bn * 9 + threadIdx.x) : __ldg(trans + bn * 3 + threadIdx.x - 9);
-    __syncthreads();
-  }
+  // camera matrix -> shared memory; the barrier that publishes it sits BEHIND the first pass's loads (below), so its
+  // memory round trip overlaps theirs
+  float cam_val = 0.f;
+  if (prm.from_geometry && threadIdx.x < 12)
+    cam_val = threadIdx.x < 9 ? __ldg(rots + bn * 9 + threadIdx.x) : __ldg(trans + bn * 3 + threadIdx.x - 9);
   // ---- stage ranks / depths of the block: WB consecutive w per (d, h) (8: one 32-byte sector); a warp covers
   //      32 / (4 * WB) bins per pass
   for (int i = threadIdx.x; i < (d_pad - prm.d) * WB; i += kScThreads) {
@@ -133,6 +133,10 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
         }
       }
       if (prm.from_geometry) {
+        if (d0 == 0) {   // CTA-uniform
+          if (threadIdx.x < 12) s_cam[threadIdx.x] = cam_val;
+          __syncthreads();
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int dd = d0 + (k * kScWarps + warp) * BPI + bs;

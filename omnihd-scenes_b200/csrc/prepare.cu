@@ -160,19 +160,36 @@ point_rank_kernel(const float* __restrict__ coor, const float* __restrict__ frus
   uint32_t kept = 0;
   for (int r = 0; r < plan.rounds; ++r) {
     const int64_t base = tile_base + (int64_t)r * kSortRound + warp * (32 * kSortItems) + lane;
-#pragma unroll 2
+    // all loads of the round first: the index arithmetic below branches (guard band, range tests) and loads do not move
+    // across branches — issued per point they cost one memory round trip each
+    float px[kSortItems], py[kSortItems], pz[kSortItems];
+    int cams[kSortItems];
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+      const int64_t idx = base + j * 32;
+      px[j] = py[j] = pz[j] = 0.f;
+      cams[j] = 0;
+      if (idx < g.n_points) {
+        cams[j] = (int)(((uint64_t)(uint32_t)idx * g.dhw_mul) >> g.dhw_shift);   // b*N + n
+        if (FROM_COOR) {
+          px[j] = ldg_stream_f32(coor + 3 * idx + 0);
+          py[j] = ldg_stream_f32(coor + 3 * idx + 1);
+          pz[j] = ldg_stream_f32(coor + 3 * idx + 2);
+        } else {
+          const int64_t o = idx - (int64_t)cams[j] * g.dhw;
+          px[j] = __ldg(frustum + 3 * o + 0);
+          py[j] = __ldg(frustum + 3 * o + 1);
+          pz[j] = __ldg(frustum + 3 * o + 2);
+        }
+      }
+    }
+#pragma unroll
     for (int j = 0; j < kSortItems; ++j) {
       const int64_t idx = base + j * 32;
       if (idx >= g.n_points) continue;
-      const int cam = (int)(((uint64_t)(uint32_t)idx * g.dhw_mul) >> g.dhw_shift);   // b*N + n
-      float x, y, z;
-      if (FROM_COOR) {
-        x = ldg_stream_f32(coor + 3 * idx + 0);
-        y = ldg_stream_f32(coor + 3 * idx + 1);
-        z = ldg_stream_f32(coor + 3 * idx + 2);
-      } else {
-        cam_point(frustum, s_cam + cam * 12, idx - (int64_t)cam * g.dhw, x, y, z);
-      }
+      const int cam = cams[j];
+      float x = px[j], y = py[j], z = pz[j];
+      if (!FROM_COOR) cam_point_of(px[j], py[j], pz[j], s_cam + cam * 12, x, y, z);
       int vx, vy, vz;
       const bool ok = voxel_index(x, g.lo[0], g.dx[0], g.inv[0], g.nx, vx) & voxel_index(y, g.lo[1], g.dx[1], g.inv[1], g.ny, vy) &
                       voxel_index(z, g.lo[2], g.dx[2], g.inv[2], g.nz, vz);
