@@ -600,9 +600,14 @@ static int backward_column_launch_w(const void* og, void* dg, void* fg, const vo
 template <typename T, int K4, bool K2>
 static int backward_column_launch(const void* og, void* dg, void* fg, const void* depth, const void* feat,
                                   const int* point_rank, int bn, const ColParams& prm, cudaStream_t st) {
-  // Measured dispatch rule: on deep frusta (cfg 3: D = 118, 32 x 88 features) the joint kernel is faster even when the
-  // tile fits twice per SM (bf16: 152 vs 169 us), so tiles deeper than 64 bins stay with it (profiles/r2_ncu_cfg3.md).
-  if (prm.d > 64) return BEVPOOL_ERR_BAD_ARG;
+  // Deep frusta (cfg 3: D = 118) take the 8-column kernel as long as two CTAs fit an SM (the shared-memory test in
+  // backward_column_launch_w): 146 us against 152 us for the joint kernel at B = 4, 265 against 286 us in the step at
+  // B = 8 (before the staging / loop clean-up of this round the joint kernel won there, 152 vs 169 us).
+  static const int max_d = [] {
+    const char* e = getenv("BEVPOOL_BWD_COLUMN_MAXD");   // measurement only
+    return e ? atoi(e) : 248;
+  }();
+  if (prm.d > max_d) return BEVPOOL_ERR_BAD_ARG;
   // 16-column tiles (64-byte pieces of depth / point_rank / the gradients per (d, h): half the L1 wavefronts of staging
   // and write-out) when they cover the image width as tightly as 8-column tiles do. BEVPOOL_BWD_TILE_W=8|16 overrides
   // (measurement only).
