@@ -944,6 +944,32 @@ def test_fused_path_ragged_feature_map(pkg, orc, zb, C):
         assert rel_to_max(f.grad.permute(0, 1, 3, 4, 2).cpu().numpy(), gf) <= TOL
 
 
+@pytest.mark.parametrize("fw,C,dt,roll", [(12, 80, torch.float32, 0.0), (28, 32, torch.float32, 0.3), (28, 64, torch.bfloat16, 0.0),
+                                            (20, 80, torch.float32, 0.0)])
+def test_column_backward_wide_and_narrow_tiles_small(pkg, orc, fw, C, dt, roll):
+    """Small Z = 1 cases for both tile widths of the column backward: fW = 12 / 28 take the 16-column kernel (128-bit
+    staging loads, one lane per (column, bin), raw ranks parked in the row ring; ragged last tile of 12 columns),
+    fW = 20 the 8-column kernel (W % 16 leaves a tighter cover with 8-column tiles); fH = 6 (partial 16-row tile), D = 9
+    (pad bins), a rolled camera (mixed bins -> slow path), bf16. BEVPOOL_BWD_TILE_W=8|16 (read once per process) forces
+    either kernel onto every shape: profiles/sanitize.sh runs this test under both settings as well."""
+    cfg = pkg.synthetic.ViewConfig("wide", (96, 16 * fw), 16, (1.0, 46.0, 5.0), (-25.6, 25.6, 0.8), (-25.6, 25.6, 0.8),
+                                   (-5.0, 3.0, 8.0), C, 2, n_cams=2)
+    B = 2
+    view, rots, trans, coor, (rb, rd, rf, st, ln), depth, feat, gout = synth_pool_case(pkg, orc, cfg, B, seed=9, roll=roll)
+    assert (view.fH, view.fW, view.D) == (6, fw, 9)
+    depth, feat, gout = (t.to(dt).float() for t in (depth, feat, gout))       # the oracle sees the rounded inputs
+    feat_cl = feat.permute(0, 1, 3, 4, 2).contiguous().numpy()
+    gd, gf = orc.bev_pool_v2_backward(gout.permute(0, 2, 3, 4, 1).contiguous().numpy(), depth.numpy(), feat_cl,
+                                      rd, rf, rb, exact=True)
+    tol = TOL if dt == torch.float32 else TOL_BF16
+    view = view.to(DEV)
+    d, f = depth.to(DEV, dt).requires_grad_(), feat.to(DEV, dt).requires_grad_()
+    bev = view(d, f, rots.to(DEV), trans.to(DEV))
+    bev.backward(gout.to(DEV, dt))
+    assert rel_to_max(d.grad.float().cpu().numpy(), gd) <= tol
+    assert rel_to_max(f.grad.float().permute(0, 1, 3, 4, 2).cpu().numpy(), gf) <= tol
+
+
 # ------------------------------------------------------------------------------------------ cross-modal fusion (§8(f) rank 4)
 def test_cross_modal_fusion_vs_reference_golden(pkg):
     """Cross_Modal_Fusion mirror with the reference's attention-conv weights: its `fuse` (everything before the final
