@@ -48,6 +48,18 @@ __device__ __forceinline__ void red_add_f32(float* p, float v) {
 }
 
 
+#ifdef BEVPOOL_TIMELINE   // measurement builds only (profiles/timeline_scatter.py): per-CTA phase stamps in ns
+__device__ unsigned long long g_sc_timeline[8 * 4096];
+__device__ __forceinline__ unsigned long long sc_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define SC_STAMP(k) do { if (threadIdx.x == 0) tl[k] = sc_now(); } while (0)
+#else
+#define SC_STAMP(k) do { } while (0)
+#endif
+
 template <bool X>
 __device__ __forceinline__ void frag_red(float* row, int sl, const Frag<X>& a) {
   red_add_f32x4(row + 4 * sl, a.v);
@@ -90,6 +102,10 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
   const int hw = prm.h * prm.w;
   const int64_t img_base = (int64_t)bn * prm.d * hw;
   pdl_wait();
+#ifdef BEVPOOL_TIMELINE
+  unsigned long long tl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+  SC_STAMP(0);
   // camera matrix -> shared memory; the barrier that publishes it sits BEHIND the first pass's loads (below), so its
   // memory round trip overlaps theirs
   float cam_val = 0.f;
@@ -132,6 +148,7 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
           }
         }
       }
+      SC_STAMP(1);   // loads of the pass issued
       if (prm.from_geometry) {
         if (d0 == 0) {   // CTA-uniform
           if (threadIdx.x < 12) s_cam[threadIdx.x] = cam_val;
@@ -152,6 +169,7 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
           }
         }
       }
+      SC_STAMP(2);   // geometry + ranks of the pass done
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int dd = d0 + (k * kScWarps + warp) * BPI + bs;
@@ -168,7 +186,9 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
       }
     }
   }
+  SC_STAMP(3);
   __syncthreads();
+  SC_STAMP(4);
 
   const int wcol = warp % WB, half = warp / WB;
   const int ww = w0 + wcol;   // this warp's image column
@@ -207,6 +227,10 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
   // every shared-memory access has an immediate offset. (Routing the summaries through a warp reduction to get
   // them into uniform registers removes the BSSY/BSYNC bookkeeping but CREDUX costs as much: measured equal.)
   int cur0 = -1;
+#ifdef BEVPOOL_TIMELINE
+  if (__any_sync(kFullMask, fv[0].v.x == 1.2345e33f)) tl[7] = 1;   // feature rows have landed
+#endif
+  SC_STAMP(5);
   for (int d0 = d_lo; d0 < d_hi; d0 += 4 * G) {
     int lead[4];
     float4 dp[4];
@@ -249,6 +273,18 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
     for (int p = 0; p < kScH; ++p)
       if (cur[p] >= 0) frag_red<X>(acc_grid + (int64_t)cur[p] * C, sc, acc[p]);
   }
+#ifdef BEVPOOL_TIMELINE
+  if (threadIdx.x == 0) {
+    const int slot = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (slot < 4096) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      tl[6] = sc_now();
+      tl[7] = smid;
+      for (int k = 0; k < 8; ++k) g_sc_timeline[8 * slot + k] = tl[k];
+    }
+  }
+#endif
 }
 
 // fp32 [F][V][C] -> T [F][C][V]; a CTA moves all channels of 64 consecutive voxels, 128-bit on both sides.
@@ -421,3 +457,10 @@ extern "C" int bevpool_view_forward(const void* depth, const void* feat, const f
   return view_forward_t<__nv_bfloat16>(depth, feat, frustum, rots, trans, prm, point_rank, out, n_frames, rows_per_frame,
                                        layout, scratch, st);
 }
+
+#ifdef BEVPOOL_TIMELINE
+extern "C" int bevpool_debug_scatter_timeline(unsigned long long* host_out, int n) {
+  cudaMemcpyFromSymbol(host_out, bevpool::g_sc_timeline, sizeof(unsigned long long) * 8 * (n < 4096 ? n : 4096));
+  return (int)cudaGetLastError();
+}
+#endif
