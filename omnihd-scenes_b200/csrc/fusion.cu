@@ -54,19 +54,30 @@ channel_avg_max_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, int* __
     mx[k] = 0.f;
     am[k] = -1;
   }
-#pragma unroll 4
-  for (int ch = warp; ch < c; ch += kFuWarps) {
-    float v[V];
+  // eight channels per warp are requested before any is consumed: the max / argmax update is data-dependent control
+  // flow, and loads do not move across it (one memory round trip per channel otherwise)
+  constexpr int kBatch = 8;
+  for (int ch0 = warp; ch0 < c; ch0 += kBatch * kFuWarps) {
+    float v[kBatch][V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) v[k] = 0.f;
-    if (in) PixIO<T, V>::load(xp + (int64_t)ch * hw, v);
+    for (int u = 0; u < kBatch; ++u) {
+      const int ch = ch0 + u * kFuWarps;
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      sum[k] += v[k];
-      // the first maximum wins; the first NaN wins and sticks (torch.max semantics)
-      if (am[k] < 0 || v[k] > mx[k] || (v[k] != v[k] && mx[k] == mx[k])) {
-        mx[k] = v[k];
-        am[k] = ch;
+      for (int k = 0; k < V; ++k) v[u][k] = 0.f;
+      if (in && ch < c) PixIO<T, V>::load(xp + (int64_t)ch * hw, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int ch = ch0 + u * kFuWarps;
+      if (ch >= c) break;   // warp-uniform
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        sum[k] += v[u][k];
+        // the first maximum wins; the first NaN wins and sticks (torch.max semantics)
+        if (am[k] < 0 || v[u][k] > mx[k] || (v[u][k] != v[u][k] && mx[k] == mx[k])) {
+          mx[k] = v[u][k];
+          am[k] = ch;
+        }
       }
     }
   }

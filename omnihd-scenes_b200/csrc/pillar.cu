@@ -42,12 +42,26 @@ pillar_canvas_kernel(const T* __restrict__ feats, const int* __restrict__ pillar
   const bool vec_in = (c & 3) == 0 && (((uintptr_t)feats) & 15) == 0;
   if (vec_in) {   // pillar rows as 128-bit pieces (a row is c*e contiguous bytes)
     const int c4 = c >> 2;
-    for (int i = threadIdx.x; i < ncol * c4; i += 256) {
-      const int col = i / c4, q = i - col * c4;
-      const int p = s_idx[col];
-      const float4 v = p >= 0 ? Vec4<T>::load_stream(feats, (int64_t)p * c + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float* o = t + (4 * q) * (kPcCols + 1) + col;
-      o[0] = v.x; o[kPcCols + 1] = v.y; o[2 * (kPcCols + 1)] = v.z; o[3 * (kPcCols + 1)] = v.w;
+    // four row pieces per thread are requested before any is stored (a load and its dependent shared-memory stores per
+    // iteration would cost one memory round trip each: 64 cells x 64 channels are 4 iterations per thread)
+    for (int i0 = threadIdx.x; i0 < ncol * c4; i0 += 4 * 256) {
+      float4 v[4];
+      int col[4], q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 256;
+        col[u] = i / c4;
+        q[u] = i - col[u] * c4;
+        const int p = i < ncol * c4 ? s_idx[col[u]] : -1;
+        v[u] = p >= 0 ? Vec4<T>::load_stream(feats, (int64_t)p * c + 4 * q[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i0 + u * 256 < ncol * c4) {
+          float* o = t + (4 * q[u]) * (kPcCols + 1) + col[u];
+          o[0] = v[u].x; o[kPcCols + 1] = v[u].y; o[2 * (kPcCols + 1)] = v[u].z; o[3 * (kPcCols + 1)] = v[u].w;
+        }
+      }
     }
   } else {
     for (int i = threadIdx.x; i < ncol * c; i += 256) {
