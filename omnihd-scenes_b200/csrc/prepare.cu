@@ -316,6 +316,20 @@ radix_scatter_kernel(const int* __restrict__ keys_in, const int* __restrict__ va
   const int64_t tile_base = (int64_t)blockIdx.x * tile_keys;
   if (tile_base >= n) return;
 
+  // the first round's keys are requested before the digit-base prologue (a scan with two barriers behind its own loads):
+  // one memory round trip instead of two before the ranking can start
+  int key[kSortItems], val[kSortItems];
+  auto load_round = [&](int64_t round_base) {
+    const int64_t base = round_base + warp * (32 * kSortItems) + lane;
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+      const int64_t idx = base + j * 32;
+      key[j] = idx < n ? ldg_stream_i32(keys_in + idx) : -1;
+      val[j] = vals_in ? (idx < n ? ldg_stream_i32(vals_in + idx) : 0) : (int)idx;
+    }
+  };
+  load_round(tile_base);
+
   // digit_base = (keys with a smaller digit) + (keys with this digit in earlier tiles)
   {
     uint32_t carry = 0;
@@ -334,15 +348,8 @@ radix_scatter_kernel(const int* __restrict__ keys_in, const int* __restrict__ va
     for (int w = 0; w < kSortWarps; ++w)
       for (int d = tid; d < bins; d += kSortThreads) warp_hist[w][d] = 0;
     __syncthreads();
-    int key[kSortItems], val[kSortItems];
     uint32_t rank[kSortItems];
-    const int64_t base = round_base + warp * (32 * kSortItems) + lane;
-#pragma unroll
-    for (int j = 0; j < kSortItems; ++j) {
-      const int64_t idx = base + j * 32;
-      key[j] = idx < n ? ldg_stream_i32(keys_in + idx) : -1;
-      val[j] = vals_in ? (idx < n ? ldg_stream_i32(vals_in + idx) : 0) : (int)idx;
-    }
+    if (r > 0) load_round(round_base);
     // warp-level ranking: lanes with the same digit find each other with match.any
 #pragma unroll
     for (int j = 0; j < kSortItems; ++j) {
