@@ -132,7 +132,7 @@ int bevpool_prepare_v2(const float* coor, const float* frustum, const float* rot
 /* Same work, plus the two counts handed back to the HOST (host_counts[0] = P, host_counts[1] = I) — what the
  * reference API needs to return exact-length tensors (cam_stream_lss_bevpoolv2.py:324-351 reads them through
  * boolean-mask indexing and torch.where). P is final after the rank kernel and I equals the number of occupied
- * voxels (a bitmap filled by the same kernel), so a small kernel stores both into page-locked host memory BEFORE the sort
+ * voxels (a byte map filled by the same kernel with plain stores), so a small kernel stores both into page-locked host memory BEFORE the sort
  * and the segmentation: the call returns as soon as that kernel is done, with the remaining kernels still running on
  * `stream`. This is the only entry point that waits for the device; it refuses a capturing stream (BEVPOOL_ERR_BAD_ARG). */
 int bevpool_prepare_v2_counts(const float* coor, const float* frustum, const float* rots, const float* trans,

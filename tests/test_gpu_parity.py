@@ -243,7 +243,7 @@ def test_prepare_properties_omnihd_shape(pkg):
 
 @pytest.mark.parametrize("cfg_name,B", [("bevdet_r50_b8", 3), ("occ_200x200x16_b64", 1), ("tiny", 1)])
 def test_prepare_early_host_counts_equal_device_counts(pkg, cfg_name, B, monkeypatch):
-    """bevpool_prepare_v2_counts hands (P, I) to the host from the rank kernel's kept count and voxel bitmap, before
+    """bevpool_prepare_v2_counts hands (P, I) to the host from the rank kernel's kept count and voxel byte map, before
     the sort has run: they must equal what the sort + segmentation leave in counts_dev, and the late read-back
     (BEVPOOL_LATE_COUNTS=1) must return the same tensors."""
     vt = pkg.view_transform
