@@ -292,6 +292,28 @@ __device__ __forceinline__ bool voxel_index(float c, float lo, float dx, float i
   return in;
 }
 
+// The three axes of one point at once: ONE rarely taken branch for the guard-band / divide cases of all axes, everything
+// else straight-line (three calls of voxel_index cost three reconvergence scopes per point). Same values as voxel_index.
+__device__ __forceinline__ bool voxel_index3(float x, float y, float z, const float (&lo)[3], const float (&dx)[3],
+                                             const float (&inv)[3], int nx, int ny, int nz, int& vx, int& vy, int& vz) {
+  constexpr float kBand = 4.76837158203125e-7f;   // 2^-21
+  const float tx = __fsub_rn(x, lo[0]), ty = __fsub_rn(y, lo[1]), tz = __fsub_rn(z, lo[2]);
+  float qx = __fmul_rn(tx, fabsf(inv[0])), qy = __fmul_rn(ty, fabsf(inv[1])), qz = __fmul_rn(tz, fabsf(inv[2]));
+  const bool sx = inv[0] > 0.f || (inv[0] < 0.f && fabsf(qx - rintf(qx)) > fabsf(qx) * kBand);
+  const bool sy = inv[1] > 0.f || (inv[1] < 0.f && fabsf(qy - rintf(qy)) > fabsf(qy) * kBand);
+  const bool sz = inv[2] > 0.f || (inv[2] < 0.f && fabsf(qz - rintf(qz)) > fabsf(qz) * kBand);
+  if (!(sx && sy && sz)) {   // inside a guard band, NaN, or an axis without a usable reciprocal
+    if (!sx) qx = __fdiv_rn(tx, dx[0]);
+    if (!sy) qy = __fdiv_rn(ty, dx[1]);
+    if (!sz) qz = __fdiv_rn(tz, dx[2]);
+  }
+  const bool in = qx > -1.0f && qx < (float)nx && qy > -1.0f && qy < (float)ny && qz > -1.0f && qz < (float)nz;
+  vx = (int)(in ? qx : 0.f);
+  vy = (int)(in ? qy : 0.f);
+  vz = (int)(in ? qz : 0.f);
+  return in;
+}
+
 // see voxel_index: 1/dx if dx is a positive power of two (exact), -fl(1/dx) for any other positive finite dx, else 0
 inline float exact_reciprocal_or_zero(float dx) {
   int e = 0;

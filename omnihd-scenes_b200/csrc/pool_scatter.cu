@@ -123,8 +123,11 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
     const unsigned colmask = (WB == 8 ? 0x01010101u : 0x00001111u) << (wl + 4 * WB * bs);
     const bool in = h0 + hl < prm.h && w0 + wl < prm.w;
     const int pix = (h0 + hl) * prm.w + w0 + wl;
-    const int64_t vpf = (int64_t)prm.nx * prm.ny * prm.nz;
-    const int64_t frame_base = (int64_t)(bn / prm.n_cams) * vpf;
+    // 32-bit arithmetic throughout the staging loop: ranks fit int32 (checked by the launcher) and offsets inside one image
+    // too; the 64-bit image base is folded into three pointers once
+    const int frame_base = (bn / prm.n_cams) * (prm.nx * prm.ny * prm.nz);
+    const T* depth_img = depth + img_base;
+    int* rank_img = point_rank + img_base;
     for (int d0 = 0; d0 < prm.d; d0 += 4 * kScWarps * BPI) {
       int r[4];
       float dv[4];
@@ -137,14 +140,15 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
         r[k] = -1;
         dv[k] = fu[k] = fv[k] = fd[k] = 0.f;
         if (in && dd < prm.d) {
-          const int64_t o = (int64_t)dd * hw + pix;
-          dv[k] = Vec4<T>::load1(depth, img_base + o);
+          const int o = dd * hw + pix;
+          dv[k] = Vec4<T>::load1(depth_img, o);
           if (prm.from_geometry) {
-            fu[k] = __ldg(frustum + 3 * o + 0);
-            fv[k] = __ldg(frustum + 3 * o + 1);
-            fd[k] = __ldg(frustum + 3 * o + 2);
+            const float* fp = frustum + 3 * o;
+            fu[k] = __ldg(fp + 0);
+            fv[k] = __ldg(fp + 1);
+            fd[k] = __ldg(fp + 2);
           } else {
-            r[k] = ldg_stream_i32(point_rank + img_base + o);
+            r[k] = ldg_stream_i32(rank_img + o);
           }
         }
       }
@@ -157,16 +161,14 @@ view_fwd_scatter_kernel(const T* __restrict__ depth, const T* __restrict__ feat,
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int dd = d0 + (k * kScWarps + warp) * BPI + bs;
-          if (in && dd < prm.d) {
-            float x, y, z;
-            cam_point_of(fu[k], fv[k], fd[k], s_cam, x, y, z);
-            int vx, vy, vz;
-            const bool ok = voxel_index(x, prm.lo[0], prm.dx[0], prm.inv[0], prm.nx, vx) &
-                            voxel_index(y, prm.lo[1], prm.dx[1], prm.inv[1], prm.ny, vy) &
-                            voxel_index(z, prm.lo[2], prm.dx[2], prm.inv[2], prm.nz, vz);
-            if (ok) r[k] = (int)(frame_base + ((int64_t)vz * prm.ny + vy) * prm.nx + vx);
-            point_rank[img_base + (int64_t)dd * hw + pix] = r[k];
-          }
+          // computed for every lane (out-of-range lanes hold zeros): no reconvergence scope around the arithmetic
+          float x, y, z;
+          cam_point_of(fu[k], fv[k], fd[k], s_cam, x, y, z);
+          int vx, vy, vz;
+          const bool ok = voxel_index3(x, y, z, prm.lo, prm.dx, prm.inv, prm.nx, prm.ny, prm.nz, vx, vy, vz);
+          const bool live = in && dd < prm.d;
+          r[k] = (ok && live) ? frame_base + (vz * prm.ny + vy) * prm.nx + vx : -1;
+          if (live) rank_img[dd * hw + pix] = r[k];
         }
       }
       SC_STAMP(2);   // geometry + ranks of the pass done

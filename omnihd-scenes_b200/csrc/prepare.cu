@@ -196,8 +196,7 @@ point_rank_kernel(const float* __restrict__ coor, const float* __restrict__ frus
         cam_point_of(px[j], py[j], pz[j], s_cam + cam * 12, x, y, z);
       }
       int vx, vy, vz;
-      const bool ok = voxel_index(x, g.lo[0], g.dx[0], g.inv[0], g.nx, vx) & voxel_index(y, g.lo[1], g.dx[1], g.inv[1], g.ny, vy) &
-                      voxel_index(z, g.lo[2], g.dx[2], g.inv[2], g.nz, vz);
+      const bool ok = voxel_index3(x, y, z, g.lo, g.dx, g.inv, g.nx, g.ny, g.nz, vx, vy, vz);
       int rank = -1;
       if (ok) {
         rank = (int)((int64_t)(cam / g.n_cams) * vpf + ((int64_t)vz * g.ny + vy) * g.nx + vx);
