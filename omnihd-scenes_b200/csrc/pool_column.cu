@@ -525,7 +525,9 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
     if (ww < prm.w) {
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        float* t = s_tile + (4 * rg + p) * kCgW + warp;
+        // column index XOR (row >> 2): the four row groups of a warp would otherwise hit the same banks (both lane
+        // coordinates step by 4); the reader below undoes it
+        float* t = s_tile + (4 * rg + p) * kCgW + (warp ^ rg);
 #pragma unroll
         for (int k = 0; k < K4; ++k) {
           t[(32 * k + 4 * cg + 0) * TS] = fg[p].v[k].x;
@@ -546,7 +548,7 @@ pool_bwd_column_kernel(const T* __restrict__ og, const T* __restrict__ depth, co
         const int c = cr / KS, trow = HL * (cr % KS) + hl;
         if (h0 + trow < prm.h)
           Vec4<T>::store1s(feat_grad, ((int64_t)bn * C + c) * hw + (h0 + trow) * prm.w + w0 + wl,
-                           s_tile[c * TS + trow * kCgW + wl]);
+                           s_tile[c * TS + trow * kCgW + (wl ^ (trow >> 2))]);
       }
     }
   } else if (ww < prm.w) {
